@@ -1,0 +1,416 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] (16-bit, K-major) x W[N,K]^T (16-bit, K-major), fp32 accumulate in TMEM )
+//
+// One CTA per SM loops over 128 x BN output tiles. Warp roles: warp 0 = TMA producer, warp 1 = MMA
+// issuer (one elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers ->
+// swizzled smem staging -> TMA store / TMA reduce-add). Two TMEM accumulator stages let the epilogue of
+// tile i overlap the main loop of tile i+1.
+//
+// Reference call sites this replaces (all via torch.nn on the reference side):
+//   qkv   iggt/layers/attention.py:52-58   (+ q/k LayerNorm(64) and 2-D RoPE, rope.py:154-188)
+//   proj  iggt/layers/attention.py:74-75 + layer_scale.py:27 + block.py:105 (residual)
+//   fc1   iggt/layers/mlp.py:35-36 (exact-erf GELU)      fc2  mlp.py:38 + block.py:106
+//   1x1 / 3x3 convolutions of the dense heads, iggt/heads/dpt_head.py:234-316
+#pragma once
+#include "ptx.cuh"
+
+namespace iggt {
+
+enum GemmEpi : int {
+  EPI_STORE16 = 0,   // out16 = act(acc + bias) [+ addend]
+  EPI_RESID32 = 1,   // out32 += gamma * (acc + bias)           (TMA reduce-add into the fp32 residual)
+  EPI_QKV = 2,       // out16 = [rope(ln(q)) | rope(ln(k)) | v]  (per 64-wide head)
+  EPI_STORE32 = 3,   // out32 = acc + bias
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  const float* bias;   // [N] or nullptr
+  const float* gamma;  // [N] (EPI_RESID32) or nullptr (=1)
+  int act;             // 0 none, 1 exact GELU, 2 ReLU, 3 LeakyReLU(0.01)
+  // EPI_QKV
+  int qk_norm;         // apply LayerNorm(64) (eps 1e-5, affine) + RoPE to the q and k column ranges
+  int C;               // embedding width: q = cols [0,C), k = [C,2C), v = [2C,3C)
+  const float* qn_w; const float* qn_b; const float* kn_w; const float* kn_b;  // [64]
+  const float* rope_cos; const float* rope_sin;  // [npos][16]
+  const int* pos_yx;   // [T][2] (y,x) RoPE positions of one view's tokens
+  int T;               // tokens per view (row r of A is token r % T)
+  // optional elementwise addend (EPI_STORE16): out += addend[(row % add_rows) * add_ld + col] (16-bit)
+  const void* addend; int add_rows; int add_ld;
+  // convolution mode (A is an NHWC tensor; K loop runs taps x C/64)
+  int conv_taps;       // 1 (1x1 through the 4-D path) or 9 (3x3, pad 1)
+  int conv_C;          // input channels
+  int H, W, NB;        // spatial size / images
+  int tiles_x, tiles_y;
+  // residual for conv epilogue: out += resid16[pixel, col] (NHWC, same H,W, ld = N)
+  const void* resid;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int CONV_TW = 16;
+constexpr int CONV_TH = 8;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = 16384;                 // 128 rows x 128 B staging tile
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <bool BF16>
+__device__ __forceinline__ float cvt16_to_f32(uint16_t h) {
+  if constexpr (BF16) return __uint_as_float(static_cast<uint32_t>(h) << 16);
+  else return __half2float(__ushort_as_half(h));
+}
+template <bool BF16>
+__device__ __forceinline__ float round16(float x) {
+  if constexpr (BF16) return __bfloat162float(__float2bfloat16_rn(x));
+  else return __half2float(__float2half_rn(x));
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return gelu_erf(x);
+  if (act == 2) return fmaxf(x, 0.0f);
+  if (act == 3) return x > 0.0f ? x : 0.01f * x;
+  return x;
+}
+
+// CONV: A operand comes from a 4-D NHWC tensor map (box {64, TW, TH, 1}); otherwise 2-D [M,K].
+template <int BN, int EPI, bool BF16, bool CONV>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using SM = GemmSmem<BN>;
+  constexpr int STAGES = SM::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * SM::A_BYTES;
+  uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * SM::STG_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile % p.num_n_tiles;
+        int img = 0, y0 = 0, x0 = 0;
+        if constexpr (CONV) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          img = mt / per_img;
+          const int r = mt % per_img;
+          y0 = (r / p.tiles_x) * CONV_TH;
+          x0 = (r % p.tiles_x) * CONV_TW;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+          if constexpr (CONV) {
+            const int cblocks = p.conv_C / GEMM_BK;
+            const int tap = kb / cblocks;
+            const int c0 = (kb % cblocks) * GEMM_BK;
+            int dy = 0, dx = 0;
+            if (p.conv_taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            tma_load_4d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], c0, x0 + dx, y0 + dy, img);
+          } else {
+            tma_load_2d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM);
+          }
+          tma_load_2d(smem_b + stage * SM::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, BF16, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * SM::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * SM::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = make_desc_sw128(a_addr + k * 32, 1024);
+            const uint64_t db = make_desc_sw128(b_addr + k * 32, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (128 threads, 1 row each)
+    const int ew = warp - 4;               // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;        // row inside the tile
+    const bool leader = (threadIdx.x == 128);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t store_count = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles;
+      const int nt = tile % p.num_n_tiles;
+      const int n0 = nt * BN;
+      int img = 0, y0 = 0, x0 = 0;
+      long grow;                           // global row (pixel) index of this thread, -1 if out of range
+      if constexpr (CONV) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        img = mt / per_img;
+        const int r = mt % per_img;
+        y0 = (r / p.tiles_x) * CONV_TH;
+        x0 = (r % p.tiles_x) * CONV_TW;
+        const int yy = y0 + row / CONV_TW, xx = x0 + row % CONV_TW;
+        grow = (yy < p.H && xx < p.W) ? ((long)img * p.H + yy) * p.W + xx : -1;
+      } else {
+        grow = (long)mt * GEMM_BM + row;
+        if (grow >= p.M) grow = -1;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+
+      if constexpr (EPI == EPI_STORE16 || EPI == EPI_QKV) {
+#pragma unroll 1
+        for (int c64 = 0; c64 < BN / 64; ++c64) {
+          const int col0 = n0 + c64 * 64;
+          if (col0 >= p.N) break;
+          uint8_t* stg = staging + (store_count & 1) * SM::STG_BYTES;
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          float v[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_row + c64 * 64, r0);
+            tmem_ld_32x32(t_row + c64 * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+          }
+          if (c64 == BN / 64 - 1 || col0 + 64 >= p.N) {
+            // last TMEM read of this tile: release the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              if (col0 + i < p.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            }
+          }
+          if constexpr (EPI == EPI_QKV) {
+            if (p.qk_norm && col0 < 2 * p.C) {
+              const bool is_k = col0 >= p.C;
+              const float* nw = is_k ? p.kn_w : p.qn_w;
+              const float* nb = is_k ? p.kn_b : p.qn_b;
+              // the reference rounds the Linear output to 16 bit before the fp32 LayerNorm (autocast)
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) { v[i] = round16<BF16>(v[i]); s += v[i]; }
+              const float mean = s * (1.0f / 64.0f);
+              float q = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; q += d * d; }
+              const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(nw + i) + __ldg(nb + i);
+              // 2-D RoPE: dims [0,32) rotate with the y position, [32,64) with x; halves of 16
+              const int t = (grow >= 0) ? static_cast<int>(grow % p.T) : 0;
+              const int py = __ldg(p.pos_yx + 2 * t), px = __ldg(p.pos_yx + 2 * t + 1);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int ps = h == 0 ? py : px;
+                const float* cs = p.rope_cos + ps * 16;
+                const float* sn = p.rope_sin + ps * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float c = __ldg(cs + i), s_ = __ldg(sn + i);
+                  const float a = v[h * 32 + i], b = v[h * 32 + 16 + i];
+                  v[h * 32 + i] = a * c - b * s_;
+                  v[h * 32 + 16 + i] = b * c + a * s_;
+                }
+              }
+            }
+          } else {
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = apply_act(v[i], p.act);
+            }
+            if (p.addend && grow >= 0) {
+              const uint16_t* ad = reinterpret_cast<const uint16_t*>(p.addend) +
+                                   (grow % p.add_rows) * (long)p.add_ld + col0;
+#pragma unroll
+              for (int i = 0; i < 64; i += 8) {
+                if (col0 + i < p.N) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(ad + i));
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    v[i + 2 * j] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] & 0xFFFF));
+                    v[i + 2 * j + 1] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] >> 16));
+                  }
+                }
+              }
+            }
+            if constexpr (CONV) {
+              if (p.resid && grow >= 0) {
+                const uint16_t* ad = reinterpret_cast<const uint16_t*>(p.resid) + grow * (long)p.N + col0;
+#pragma unroll
+                for (int i = 0; i < 64; i += 8) {
+                  if (col0 + i < p.N) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ad + i));
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      v[i + 2 * j] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] & 0xFFFF));
+                      v[i + 2 * j + 1] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] >> 16));
+                    }
+                  }
+                }
+              }
+            }
+          }
+          // registers -> 128B-swizzled staging tile (row = 128 B = 64 x 16 bit)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            u.x = pack16x2<BF16>(v[c * 8 + 0], v[c * 8 + 1]);
+            u.y = pack16x2<BF16>(v[c * 8 + 2], v[c * 8 + 3]);
+            u.z = pack16x2<BF16>(v[c * 8 + 4], v[c * 8 + 5]);
+            u.w = pack16x2<BF16>(v[c * 8 + 6], v[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            if constexpr (CONV) tma_store_4d(&tmC, stg, col0, x0, y0, img);
+            else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
+            tma_store_commit();
+          }
+          ++store_count;
+        }
+      } else {
+        // fp32 outputs: 32 columns (128 B) per staging tile
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+          const int col0 = n0 + c32 * 32;
+          if (col0 >= p.N) break;
+          uint8_t* stg = staging + (store_count & 1) * SM::STG_BYTES;
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint32_t r0[32];
+          tmem_ld_32x32(t_row + c32 * 32, r0);
+          tmem_ld_wait();
+          if (c32 == BN / 32 - 1 || col0 + 32 >= p.N) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (col0 + i < p.N) {
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+              if constexpr (EPI == EPI_RESID32) {
+                if (p.gamma) {
+                  const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i));
+                  v[i] *= g.x; v[i + 1] *= g.y; v[i + 2] *= g.z; v[i + 3] *= g.w;
+                }
+              }
+            }
+          }
+          if constexpr (EPI == EPI_STORE32) {
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 u = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+            *reinterpret_cast<float4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            if constexpr (EPI == EPI_RESID32) tma_reduce_add_2d(&tmC, stg, col0, mt * GEMM_BM);
+            else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
+            tma_store_commit();
+          }
+          ++store_count;
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+}  // namespace iggt

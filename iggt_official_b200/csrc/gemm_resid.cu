@@ -1,0 +1,68 @@
+// C-ABI launchers: residual (TMA reduce-add) and fused qkv + q/k-LayerNorm + RoPE epilogues.
+#include "gemm_launch.cuh"
+#include "../../include/iggt_b200.h"
+
+using namespace iggt;
+
+namespace {
+template <int EPI, bool BF16>
+int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                const GemmParams& p, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch_gemm_kernel<256, EPI, BF16, false>(tA, tB, tC, p, s);
+    default: return launch_gemm_kernel<128, EPI, BF16, false>(tA, tB, tC, p, s);
+  }
+}
+}  // namespace
+
+extern "C" int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int64_t ldw, float* x,
+                                 int64_t ldx, int M, int N, int K, int dtype, const float* bias,
+                                 const float* gamma, iggt_stream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  if ((lda % 8) || (ldw % 8) || (K % 8) || (ldx % 4) || (N % 4)) return -2;
+  if (dtype != 0 && dtype != 1) return -3;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma;
+  p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  int bn = choose_bn(p.num_m_tiles, N);
+  if (bn < 128) bn = 128;
+  p.num_n_tiles = (N + bn - 1) / bn;
+  p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const TmDtype dt = dtype ? TM_BF16 : TM_F16;
+  CUtensorMap tA, tB, tC;
+  if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
+  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, bn)) return -4;
+  if (make_tmap_2d(&tC, TM_F32, x, M, N, ldx, 32, GEMM_BM)) return -4;
+  return dtype ? dispatch_bn<EPI_RESID32, true>(bn, tA, tB, tC, p, (cudaStream_t)stream)
+               : dispatch_bn<EPI_RESID32, false>(bn, tA, tB, tC, p, (cudaStream_t)stream);
+}
+
+extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv,
+                             int64_t ldo, int M, int C, int K, int dtype, const float* bias,
+                             int qk_norm, const float* qn_w, const float* qn_b, const float* kn_w,
+                             const float* kn_b, const float* rope_cos, const float* rope_sin,
+                             const int* pos_yx, int T, iggt_stream_t stream) {
+  if (M <= 0 || C <= 0 || K <= 0 || (C % 64)) return -1;
+  if ((lda % 8) || (ldw % 8) || (K % 8) || (ldo % 8)) return -2;
+  if (dtype != 0 && dtype != 1) return -3;
+  if (qk_norm && (!qn_w || !qn_b || !kn_w || !kn_b || !rope_cos || !rope_sin || !pos_yx || T <= 0))
+    return -5;
+  const int N = 3 * C;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias;
+  p.qk_norm = qk_norm; p.C = C;
+  p.qn_w = qn_w; p.qn_b = qn_b; p.kn_w = kn_w; p.kn_b = kn_b;
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.pos_yx = pos_yx; p.T = T > 0 ? T : 1;
+  p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  int bn = choose_bn(p.num_m_tiles, N);
+  if (bn < 128) bn = 128;
+  p.num_n_tiles = (N + bn - 1) / bn;
+  p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const TmDtype dt = dtype ? TM_BF16 : TM_F16;
+  CUtensorMap tA, tB, tC;
+  if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
+  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, bn)) return -4;
+  if (make_tmap_2d(&tC, dt, qkv, M, N, ldo, 64, GEMM_BM)) return -4;
+  return dtype ? dispatch_bn<EPI_QKV, true>(bn, tA, tB, tC, p, (cudaStream_t)stream)
+               : dispatch_bn<EPI_QKV, false>(bn, tA, tB, tC, p, (cudaStream_t)stream);
+}

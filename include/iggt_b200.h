@@ -1,0 +1,104 @@
+/*
+ * iggt_b200.h -- C ABI of the B200-native IGGT inference kernels (libiggt_b200.so).
+ *
+ * The reference (lifuguan/IGGT_official) has no FFI on this path: everything below
+ * `IGGT.forward` (iggt/models/vggt.py:149-230) is torch.nn modules.  This header is therefore the
+ * boundary SURVEY.md 8(b) asks the builder to define: one `extern "C"` launcher per fused operator,
+ * raw device pointers + sizes + a CUDA stream, `int` return (0 = ok, <0 = argument/setup error,
+ * >0 = cudaError_t).  Each entry cites the reference call site it replaces.  All pointers are device
+ * pointers unless stated otherwise; all launches are asynchronous on `stream`.
+ *
+ * dtype: 0 = fp16, 1 = bf16 (16-bit activations / weights; accumulation is always fp32).
+ */
+#ifndef IGGT_B200_H_
+#define IGGT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* iggt_stream_t; /* cudaStream_t */
+
+/* Library / device probe. Returns 0 and fills sm (e.g. 100) and num_sms, or >0 cudaError_t. */
+int iggt_device_info(int* sm, int* num_sms);
+const char* iggt_version(void);
+
+/* ---- GEMM family (tcgen05 / TMEM / TMA).  A:[M,K] lda, W:[N,K] ldw (torch Linear layout), 16-bit. */
+
+/* out16[M,N] = act(A W^T + bias) (+ addend[(row % add_rows), :]).  act: 0 none, 1 exact-erf GELU,
+ * 2 ReLU, 3 LeakyReLU(0.01).  Replaces mlp.fc1 (iggt/layers/mlp.py:35-36), DPT `projects` 1x1 conv +
+ * pos-embed (iggt/heads/dpt_head.py:238-240), generic Linear layers. */
+int iggt_gemm_store16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                      int M, int N, int K, int dtype, const float* bias, int act,
+                      const void* addend, int add_rows, int64_t add_ld, iggt_stream_t stream);
+
+/* x32[M,N] += gamma * (A W^T + bias)   (fp32 residual stream, TMA reduce-add).
+ * Replaces attn.proj / mlp.fc2 + LayerScale + residual (iggt/layers/attention.py:74-75, mlp.py:38,
+ * layer_scale.py:27, block.py:105-106). */
+int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx,
+                      int M, int N, int K, int dtype, const float* bias, const float* gamma,
+                      iggt_stream_t stream);
+
+/* out32[M,N] = act(A W^T + bias) (fp32 output). */
+int iggt_gemm_store32(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo,
+                      int M, int N, int K, int dtype, const float* bias, int act, iggt_stream_t stream);
+
+/* qkv16[M,3C] = A Wqkv^T + bias, then (if qk_norm) per 64-wide head of the q and k column ranges:
+ * LayerNorm(64, eps 1e-5, affine) followed by 2-D RoPE (first 32 dims by y, last 32 by x, rotate-half
+ * of 16, table [npos][16]).  Row r is token r % T of its view; pos_yx[T][2] holds (y,x).
+ * Replaces iggt/layers/attention.py:52-58 + iggt/layers/rope.py:154-188. */
+int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int64_t ldo,
+                  int M, int C, int K, int dtype, const float* bias, int qk_norm,
+                  const float* qn_w, const float* qn_b, const float* kn_w, const float* kn_b,
+                  const float* rope_cos, const float* rope_sin, const int* pos_yx, int T,
+                  iggt_stream_t stream);
+
+/* 3x3 (pad 1, stride 1) or 1x1 convolution as implicit GEMM over an NHWC 16-bit tensor:
+ * out[NB,H,W,Cout] = act(conv(x[NB,H,W,Cin], Wp[Cout, taps*Cin]) + bias) (+ resid[NB,H,W,Cout]).
+ * Wp is packed tap-major: k = (ky*3+kx)*Cin + ci.  Cin % 64 == 0.
+ * Replaces the Conv2d layers of iggt/heads/dpt_head.py:298-316,369-411. */
+int iggt_conv_nhwc(const void* x, const void* Wp, void* out, int NB, int H, int W, int Cin, int Cout,
+                   int taps, int dtype, const float* bias, int act, const void* resid,
+                   iggt_stream_t stream);
+
+
+/* ---- Flash attention forward (tcgen05 QK^T / PV, TMEM accumulators, online softmax), head_dim 64.
+ * q/k/v/o: token-major [rows, ld] 16-bit, head h in columns [64h, 64h+64).  Sequence s owns q/o rows
+ * [s*Lq,(s+1)*Lq) and k/v rows [s*Lk,(s+1)*Lk).  Non-causal, no mask.
+ * Replaces F.scaled_dot_product_attention at iggt/layers/attention.py:61-66. */
+int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
+                       int head_dim, float scale, int dtype, iggt_stream_t stream);
+
+/* ---- HBM-bound trunk kernels. */
+
+/* LayerNorm over C (1024 or 2048) fp32 features, one warp per row.  Output row g*out_rows_per_group +
+ * out_off + i  <-  input row g*rows_in + in_off + i, for g < groups, i < rows_out.  w/b may be NULL.
+ * out_kind: 0 fp16, 1 bf16, 2 fp32.  Replaces nn.LayerNorm at iggt/layers/block.py:50,66,
+ * iggt/layers/vision_transformer.py:274, iggt/heads/dpt_head.py:234. */
+int iggt_layernorm(const float* x, int64_t ldx, void* y, int64_t ldy, int C, const float* w,
+                   const float* b, float eps, int64_t groups, int rows_out, int rows_in, int in_off,
+                   int out_rows_per_group, int out_off, int out_kind, iggt_stream_t stream);
+
+/* images [NI,3,H,W] fp32 in [0,1] -> A[NI*(H/14)*(W/14), KP] 16-bit im2col rows of the 14x14/s14 patch
+ * conv (k = c*196 + ky*14 + kx, zero padded to KP >= 588), fused with the ImageNet (x-mean)/std.
+ * Replaces iggt/models/aggregator.py:206 + iggt/layers/patch_embed.py:75-77 (the GEMM follows). */
+int iggt_patchify(const float* images, void* A, int NI, int H, int W, int KP, int dtype,
+                  iggt_stream_t stream);
+
+/* DINOv2 token assembly: x[n,0]=cls+pos[0]; x[n,1..R]=reg; x[n,1+R+p]=pe16[n,p]+pos[1+p]  (fp32 out).
+ * Replaces iggt/layers/vision_transformer.py:217-236. */
+int iggt_dino_assemble(const void* pe16, const float* cls, const float* reg, const float* pos, float* x,
+                       int NI, int P, int R, int C, int dtype, iggt_stream_t stream);
+
+/* Aggregator camera/register tokens into rows [n*T, n*T+1+R) of x (variant 0 for view 0 of a scene).
+ * Replaces iggt/models/aggregator.py:230-234,338-361. */
+int iggt_special_tokens(const float* cam, const float* reg, float* x, int NI, int T, int R, int C,
+                        int S_loc, int view_offset, iggt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGGT_B200_H_ */

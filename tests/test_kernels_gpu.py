@@ -1,0 +1,235 @@
+"""Per-kernel parity tests (GPU): every C-ABI launcher against a plain fp32 PyTorch statement of the
+same operator on identical (16-bit-rounded) inputs.  Tolerances are written next to each assert."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float16, torch.bfloat16]
+
+
+def _tol(dtype):
+    # one ulp of the 16-bit output format relative to the tensor's magnitude, plus fp32 reorder noise
+    return 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+
+
+def _relmax(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from iggt_official_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K,act", [(300, 320, 192, 0), (2748, 4096, 1024, 1), (128, 64, 64, 2), (77, 32, 128, 3),
+                                        (1000, 768, 2048, 0)])
+def test_gemm_store16(ops, dtype, M, N, K, act):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    ref = {0: lambda t: t, 1: lambda t: F.gelu(t), 2: F.relu, 3: lambda t: F.leaky_relu(t, 0.01)}[act](ref)
+    out = ops.gemm_store16(a, w, bias, act=act)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    assert _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_store16_addend(ops, dtype):
+    M, N, K, R = 3 * 361, 256, 2048, 361
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g)
+    add = torch.randn(R, N, device="cuda", generator=g).to(dtype)
+    ref = a.float() @ w.float().t() + bias + add.float().repeat(3, 1)
+    out = ops.gemm_store16(a, w, bias, addend=add, add_rows=R)
+    torch.cuda.synchronize()
+    assert _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (2748, 1024, 4096), (9, 2048, 2048)])
+def test_gemm_resid32(ops, dtype, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + gamma * (a.float() @ w.float().t() + bias)
+    ops.gemm_resid32(a, w, x, bias, gamma)
+    torch.cuda.synchronize()
+    # fp32 output: only accumulation-order noise (K products of 16-bit values)
+    assert _relmax(x, ref) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_store32(ops, dtype):
+    M, N, K = 137, 520, 256
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm_store32(a, w, bias)
+    torch.cuda.synchronize()
+    assert _relmax(out, ref) < 2e-5
+
+
+def _rope_tables(npos, device):
+    # iggt/layers/rope.py:103-112 with feature_dim 32, base 100
+    exponents = torch.arange(0, 32, 2, device=device).float() / 32
+    inv_freq = 1.0 / (100.0 ** exponents)
+    ang = torch.einsum("i,j->ij", torch.arange(npos, device=device, dtype=torch.float32), inv_freq)
+    return ang.cos().contiguous(), ang.sin().contiguous()
+
+
+def _rope_ref(t, pos):
+    # t [M, H, 64] fp32, pos [M, 2] long (y, x)  -- iggt/layers/rope.py:119-188
+    cos16, sin16 = _rope_tables(int(pos.max()) + 1, t.device)
+    cos = torch.cat([cos16, cos16], -1)
+    sin = torch.cat([sin16, sin16], -1)
+
+    def rot(x):
+        return torch.cat([-x[..., 16:], x[..., :16]], -1)
+
+    def one(x, p):
+        c, s = cos[p][:, None, :], sin[p][:, None, :]
+        return x * c + rot(x) * s
+
+    return torch.cat([one(t[..., :32], pos[:, 0]), one(t[..., 32:], pos[:, 1])], -1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qk_norm", [False, True])
+def test_gemm_qkv(ops, dtype, qk_norm):
+    C, K, gh, gw, S = 1024, 1024, 5, 7, 3
+    T = 5 + gh * gw
+    M = S * T
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(3 * C, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(3 * C, device="cuda", generator=g) * 0.1
+    qn_w = torch.rand(64, device="cuda", generator=g) + 0.5
+    qn_b = torch.randn(64, device="cuda", generator=g) * 0.1
+    kn_w = torch.rand(64, device="cuda", generator=g) + 0.5
+    kn_b = torch.randn(64, device="cuda", generator=g) * 0.1
+    yy, xx = torch.meshgrid(torch.arange(gh, device="cuda"), torch.arange(gw, device="cuda"), indexing="ij")
+    pos = torch.cat([torch.zeros(5, 2, dtype=torch.long, device="cuda"),
+                     torch.stack([yy.reshape(-1), xx.reshape(-1)], -1) + 1], 0)  # [T,2]
+    cos, sin = _rope_tables(max(gh, gw) + 1, "cuda")
+    out = ops.gemm_qkv(a, w, bias, C, qk_norm=qk_norm, qn_w=qn_w, qn_b=qn_b, kn_w=kn_w, kn_b=kn_b,
+                       rope_cos=cos, rope_sin=sin, pos_yx=pos.int().contiguous(), T=T)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t() + bias)
+    if qk_norm:
+        ref = ref.to(dtype).float()  # the autocast Linear output is 16-bit before the fp32 LayerNorm
+        q, k, v = ref.view(M, 3, 16, 64).unbind(1)
+        q = F.layer_norm(q, (64,), qn_w, qn_b, 1e-5)
+        k = F.layer_norm(k, (64,), kn_w, kn_b, 1e-5)
+        posm = pos.repeat(S, 1)
+        q, k = _rope_ref(q, posm), _rope_ref(k, posm)
+        ref = torch.stack([q, k, v], 1).reshape(M, 3 * C)
+    # LayerNorm(64) amplifies a 16-bit rounding flip of its input by ~1/std, so allow 4 ulp
+    assert _relmax(out, ref) < 4 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("num_seq,Lq,Lk,H", [(3, 300, 300, 4), (2, 1374, 1374, 16), (1, 200, 900, 2), (1, 128, 128, 1)])
+def test_attention(ops, dtype, num_seq, Lq, Lk, H):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    C = H * 64
+    qkv_q = torch.randn(num_seq * Lq, C, device="cuda", generator=g).to(dtype)
+    kv = torch.randn(num_seq * Lk, 2 * C, device="cuda", generator=g).to(dtype)
+    k, v = kv[:, :C], kv[:, C:]
+    out = ops.attention(qkv_q, k, v, num_seq, Lq, Lk, H)
+    torch.cuda.synchronize()
+    q4 = qkv_q.float().view(num_seq, Lq, H, 64).transpose(1, 2)
+    k4 = k.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)
+    v4 = v.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)
+    att = torch.softmax(q4 @ k4.transpose(-1, -2) * 0.125, -1) @ v4
+    ref = att.transpose(1, 2).reshape(num_seq * Lq, C)
+    # P is rounded to 16 bit before PV (as in every flash kernel): 2 ulp of the output scale
+    assert _relmax(out, ref) < 3 * _tol(dtype)
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("C", [1024, 2048])
+def test_layernorm(ops, out_dtype, C):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    G, rin, off, rout = 3, 50, 5, 45
+    x = torch.randn(G * rin, C, device="cuda", generator=g) * 3 + 1
+    w = torch.rand(C, device="cuda", generator=g) + 0.5
+    b = torch.randn(C, device="cuda", generator=g)
+    out = torch.zeros(G * rout, C, device="cuda", dtype=out_dtype)
+    ops.layernorm(x, w, b, 1e-6, out, groups=G, rows_out=rout, rows_in=rin, in_off=off)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.view(G, rin, C)[:, off:off + rout].reshape(-1, C), (C,), w, b, 1e-6)
+    tol = 1e-5 if out_dtype == torch.float32 else _tol(out_dtype)
+    assert _relmax(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,taps,act,use_res", [(2, 37, 37, 256, 256, 9, 2, True), (1, 20, 50, 64, 128, 9, 0, False),
+                                                              (2, 19, 19, 1024, 256, 9, 0, False), (1, 30, 30, 128, 32, 9, 2, False),
+                                                              (2, 37, 37, 256, 256, 1, 0, False)])
+def test_conv_nhwc(ops, dtype, NB, H, W, Cin, Cout, taps, act, use_res):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).to(dtype)
+    ks = 3 if taps == 9 else 1
+    w = (torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * taps)).to(dtype)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(NB, H, W, Cout, device="cuda", generator=g).to(dtype) if use_res else None
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, taps * Cin).contiguous()
+    out = ops.conv_nhwc(x, wp, bias, act=act, resid=res, taps=taps)
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=ks // 2)
+    if act == 2:
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    if use_res:
+        ref = ref + res.float()
+    assert _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_patchify_and_assemble(ops, dtype):
+    NI, H, W, C = 2, 42, 56, 1024
+    g = torch.Generator(device="cuda").manual_seed(13)
+    img = torch.rand(NI, 3, H, W, device="cuda", generator=g)
+    A = ops.patchify(img, 640, dtype)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    ref = F.unfold((img - mean) / std, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    torch.cuda.synchronize()
+    assert _relmax(A[:, :588], ref) < _tol(dtype)
+    assert A[:, 588:].abs().max().item() == 0
+    P, R = (H // 14) * (W // 14), 4
+    pe = torch.randn(NI * P, C, device="cuda", generator=g).to(dtype)
+    cls = torch.randn(C, device="cuda", generator=g)
+    reg = torch.randn(R, C, device="cuda", generator=g)
+    pos = torch.randn(1 + P, C, device="cuda", generator=g)
+    x = torch.empty(NI * (1 + R + P), C, device="cuda")
+    ops.dino_assemble(pe, cls, reg, pos, x, NI, P, R, C)
+    torch.cuda.synchronize()
+    refx = torch.cat([(cls + pos[0]).expand(NI, 1, C), reg.expand(NI, R, C), pe.float().view(NI, P, C) + pos[1:]], 1)
+    assert torch.equal(x.view(NI, 1 + R + P, C), refx)
+    cam = torch.randn(2, C, device="cuda", generator=g)
+    regt = torch.randn(2, R, C, device="cuda", generator=g)
+    T = 1 + R + P
+    y = torch.zeros(NI * 2 * T, C, device="cuda")  # 2 scenes x NI views
+    ops.special_tokens(cam, regt, y, NI * 2, T, R, C, NI, 0)
+    torch.cuda.synchronize()
+    y4 = y.view(2, NI, T, C)
+    assert torch.equal(y4[:, 0, 0], cam[0].expand(2, C)) and torch.equal(y4[:, 1, 0], cam[1].expand(2, C))
+    assert torch.equal(y4[:, 0, 1:1 + R], regt[0].expand(2, R, C)) and torch.equal(y4[:, 1, 1:1 + R], regt[1].expand(2, R, C))
