@@ -20,13 +20,14 @@ int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const CUte
 
 extern "C" int iggt_conv_nhwc(const void* x, const void* Wp, void* out, int NB, int H, int W,
                               int Cin, int Cout, int taps, int dtype, const float* bias, int act,
-                              const void* resid, iggt_stream_t stream) {
+                              const void* resid, const void* resid2, int act_post,
+                              iggt_stream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return -1;
   if ((Cin % 64) || (Cout % 8)) return -2;
   if (taps != 1 && taps != 9) return -1;
   if (dtype != 0 && dtype != 1) return -3;
   GemmParams p{};
-  p.bias = bias; p.act = act; p.resid = resid;
+  p.bias = bias; p.act = act; p.resid = resid; p.resid2 = resid2; p.act_post = act_post;
   p.conv_taps = taps; p.conv_C = Cin; p.H = H; p.W = W; p.NB = NB;
   p.tiles_x = (W + CONV_TW - 1) / CONV_TW;
   p.tiles_y = (H + CONV_TH - 1) / CONV_TH;

@@ -44,8 +44,13 @@ struct GemmParams {
   int conv_C;          // input channels
   int H, W, NB;        // spatial size / images
   int tiles_x, tiles_y;
-  // residual for conv epilogue: out += resid16[pixel, col] (NHWC, same H,W, ld = N)
+  // residuals for the conv epilogue: out = act_post(act(acc+bias) + resid16[pixel,col] + resid2_16[pixel,col])
+  // (NHWC, same H,W, ld = N)
   const void* resid;
+  const void* resid2;
+  int act_post;
+  // EPI_RESID32: round (acc + bias) to 16 bit before the LayerScale multiply (autocast Linear output)
+  int round_out16;
 };
 
 constexpr int GEMM_BM = 128;
@@ -287,7 +292,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           } else {
-            if (p.act) {
+            if (p.act == 1) {
+              // autocast: GELU is evaluated on the 16-bit Linear output (iggt/layers/mlp.py:35-36)
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = gelu_erf(round16<BF16>(v[i]));
+            } else if (p.act) {
 #pragma unroll
               for (int i = 0; i < 64; ++i) v[i] = apply_act(v[i], p.act);
             }
@@ -308,20 +317,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
             if constexpr (CONV) {
-              if (p.resid && grow >= 0) {
-                const uint16_t* ad = reinterpret_cast<const uint16_t*>(p.resid) + grow * (long)p.N + col0;
 #pragma unroll
-                for (int i = 0; i < 64; i += 8) {
-                  if (col0 + i < p.N) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ad + i));
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int rr = 0; rr < 2; ++rr) {
+                const void* rp = rr == 0 ? p.resid : p.resid2;
+                if (rp && grow >= 0) {
+                  const uint16_t* ad = reinterpret_cast<const uint16_t*>(rp) + grow * (long)p.N + col0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      v[i + 2 * j] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] & 0xFFFF));
-                      v[i + 2 * j + 1] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] >> 16));
+                  for (int i = 0; i < 64; i += 8) {
+                    if (col0 + i < p.N) {
+                      const uint4 u = __ldg(reinterpret_cast<const uint4*>(ad + i));
+                      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        v[i + 2 * j] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] & 0xFFFF));
+                        v[i + 2 * j + 1] += cvt16_to_f32<BF16>(static_cast<uint16_t>(w[j] >> 16));
+                      }
                     }
                   }
                 }
+              }
+              if (p.act_post) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] = apply_act(v[i], p.act_post);
               }
             }
           }
@@ -372,6 +389,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
               }
               if constexpr (EPI == EPI_RESID32) {
+                if (p.round_out16) {
+                  v[i] = round16<BF16>(v[i]); v[i + 1] = round16<BF16>(v[i + 1]);
+                  v[i + 2] = round16<BF16>(v[i + 2]); v[i + 3] = round16<BF16>(v[i + 3]);
+                }
                 if (p.gamma) {
                   const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i));
                   v[i] *= g.x; v[i + 1] *= g.y; v[i + 2] *= g.z; v[i + 3] *= g.w;

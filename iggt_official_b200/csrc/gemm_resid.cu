@@ -17,12 +17,12 @@ int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const CUte
 
 extern "C" int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int64_t ldw, float* x,
                                  int64_t ldx, int M, int N, int K, int dtype, const float* bias,
-                                 const float* gamma, iggt_stream_t stream) {
+                                 const float* gamma, int round_out16, iggt_stream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return -1;
   if ((lda % 8) || (ldw % 8) || (K % 8) || (ldx % 4) || (N % 4)) return -2;
   if (dtype != 0 && dtype != 1) return -3;
   GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma; p.round_out16 = round_out16;
   p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   int bn = choose_bn(p.num_m_tiles, N);
   if (bn < 128) bn = 128;

@@ -1,0 +1,331 @@
+// HBM-bound kernels of the dense heads and the camera head (all NHWC 16-bit activations unless noted):
+// bilinear(align_corners) upsample fused with the UV sinusoid pos-embed, deconv pixel-shuffle, stride-2
+// im2col, the per-pixel 1x1 + activation tail, a skinny (M <= 32) weight-streaming GEMM and a tiny
+// attention for the S camera tokens.  Coalesced 16-byte accesses, grid-stride loops.
+#include "ptx.cuh"
+#include "../../include/iggt_b200.h"
+
+namespace iggt {
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (BF16) {
+      f[2 * j] = __uint_as_float(w[j] << 16);
+      f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    } else {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      f[2 * j] = __low2float(h);
+      f[2 * j + 1] = __high2float(h);
+    }
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack16x2<BF16>(f[0], f[1]); u.y = pack16x2<BF16>(f[2], f[3]);
+  u.z = pack16x2<BF16>(f[4], f[5]); u.w = pack16x2<BF16>(f[6], f[7]);
+  return u;
+}
+
+// F.interpolate(mode="bilinear", align_corners=True) on NHWC (iggt/heads/dpt_head.py:251-256,478,484-509)
+// + optional pos-embed: channels [0,C/2) get tabx[x][c], [C/2,C) get taby[y][c-C/2]
+// (iggt/heads/dpt_head.py:274-284, iggt/heads/utils.py:11-108; tables are built on the host in float64).
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int NB, int h, int w,
+                         int H, int W, int C, const float* __restrict__ tabx, const float* __restrict__ taby) {
+  const int cv = C / 8;
+  const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
+  const float sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
+  const float sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv);
+    int64_t pix = i / cv;
+    const int ox = static_cast<int>(pix % W); pix /= W;
+    const int oy = static_cast<int>(pix % H);
+    const int n = static_cast<int>(pix / H);
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const uint16_t* base = x + static_cast<int64_t>(n) * h * w * C + c8 * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * w + x0) * C)), a);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * w + x1) * C)), b);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * w + x0) * C)), c);
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * w + x1) * C)), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * c[k] + lx * d[k]);
+    if (tabx) {
+      const int ch = c8 * 8, half = C / 2;
+      const float* t = ch < half ? tabx + static_cast<int64_t>(ox) * half + ch
+                                 : taby + static_cast<int64_t>(oy) * half + (ch - half);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += __ldg(t + k);
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * H + oy) * W + ox) * C + c8 * 8) = pack8<BF16>(o);
+  }
+}
+
+// ConvTranspose2d with kernel == stride (iggt/heads/dpt_head.py:85-92): the GEMM produced
+// y[pixel, (dy*k+dx)*C + co]; scatter to NHWC out[n, k*yy+dy, k*xx+dx, co].
+__global__ void __launch_bounds__(256)
+deconv_shuffle_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, int NB, int h, int w, int C, int k) {
+  const int cv = C / 8;
+  const int64_t total = static_cast<int64_t>(NB) * h * w * k * k * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv);
+    int64_t r = i / cv;
+    const int tap = static_cast<int>(r % (k * k)); r /= (k * k);
+    const int xx = static_cast<int>(r % w); r /= w;
+    const int yy = static_cast<int>(r % h);
+    const int n = static_cast<int>(r / h);
+    const int dy = tap / k, dx = tap % k;
+    const int64_t dst = ((static_cast<int64_t>(n) * h * k + yy * k + dy) * (w * k) + xx * k + dx) * cv + c8;
+    out[dst] = __ldg(y + i);
+  }
+}
+
+// im2col for the one stride-2 3x3 conv (pad 1) of each head (iggt/heads/dpt_head.py:94-97):
+// A[(n,oy,ox), tap*C + c] = x[n, 2oy+ky-1, 2ox+kx-1, c] (zero outside).
+__global__ void __launch_bounds__(256)
+im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ A, int NB, int h, int w, int C, int ho, int wo) {
+  const int cv = C / 8;
+  const int64_t total = static_cast<int64_t>(NB) * ho * wo * 9 * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv);
+    int64_t r = i / cv;
+    const int tap = static_cast<int>(r % 9); r /= 9;
+    const int ox = static_cast<int>(r % wo); r /= wo;
+    const int oy = static_cast<int>(r % ho);
+    const int n = static_cast<int>(r / ho);
+    const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<int64_t>(n) * h + iy) * w + ix) * cv + c8);
+    A[i] = v;
+  }
+}
+
+// Per-pixel tail: 1x1 conv 32 -> OC (fp32 weights) + head activation (iggt/heads/dpt_head.py:264-265,
+// iggt/heads/head_act.py:61-125).  mode 0: xyz=exp, conf=1+exp (depth); 1: xyz=sign*expm1|.|, conf=1+exp
+// (points); 2: raw, channels-first [NB,OC,H,W] (part_feat, iggt/heads/part_head.py:240-243).
+template <bool BF16, int OC>
+__global__ void __launch_bounds__(256)
+dpt_tail_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ out_main, float* __restrict__ out_conf, int64_t npix, int64_t hw, int mode) {
+  __shared__ float sw[OC * 32 + OC];
+  for (int i = threadIdx.x; i < OC * 32 + OC; i += blockDim.x) sw[i] = i < OC * 32 ? w[i] : b[i - OC * 32];
+  __syncthreads();
+  for (int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float f[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t[8];
+      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(x + pix * 32) + q), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[q * 8 + k] = t[k];
+    }
+    float o[OC];
+#pragma unroll
+    for (int c = 0; c < OC; ++c) {
+      float s = sw[OC * 32 + c];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) s = fmaf(f[k], sw[c * 32 + k], s);
+      o[c] = s;
+    }
+    if (mode == 2) {
+      const int64_t n = pix / hw, r = pix % hw;
+#pragma unroll
+      for (int c = 0; c < OC; ++c) out_main[(n * OC + c) * hw + r] = o[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < OC - 1; ++c) {
+        const float v = o[c];
+        out_main[pix * (OC - 1) + c] = mode == 0 ? expf(v) : copysignf(expm1f(fabsf(v)), v);
+      }
+      out_conf[pix] = 1.0f + expf(o[OC - 1]);
+    }
+  }
+}
+
+// out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 32 rows, fp32
+// activations, 16-bit weights streamed once (one warp per output column).  Camera head Linear layers
+// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.
+template <bool BF16, int MT>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ W, int64_t ldw,
+                   const float* __restrict__ bias, const float* __restrict__ gamma, const float* resid,
+                   int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int act) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+  const uint16_t* wr = W + static_cast<int64_t>(n) * ldw;
+  for (int k = lane * 8; k < K; k += 256) {
+    float wf[8];
+    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(wr + k)), wf);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k + 4));
+        acc[m] += a.x * wf[0] + a.y * wf[1] + a.z * wf[2] + a.w * wf[3] + b.x * wf[4] + b.y * wf[5] +
+                  b.z * wf[6] + b.w * wf[7];
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    const float bb = bias ? bias[n] : 0.f;
+    const float g = gamma ? gamma[n] : 1.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        float v = acc[m] + bb;
+        if (act == 1) v = gelu_erf(v);
+        else if (act == 2) v = fmaxf(v, 0.f);
+        else if (act == 4) v = v / (1.0f + expf(-v));  // SiLU
+        v *= g;
+        if (resid) v += resid[m * ldr + n];
+        out[m * ldo + n] = v;
+      }
+    }
+  }
+}
+
+// softmax(q k^T / sqrt(d)) v for tiny sequences (camera tokens: N <= 64 views, d <= 128), fp32.
+// qkv [B*N, 3*H*d] (q | k | v, head-major inside each), out [B*N, H*d]. One CTA per (b, head).
+__global__ void __launch_bounds__(128)
+small_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N, int H, int d, float scale) {
+  extern __shared__ float sm[];
+  float* sk = sm;                 // [N][d]
+  float* sv = sm + N * d;         // [N][d]
+  float* sp = sv + N * d;         // [4 warps][N]
+  const int b = blockIdx.x / H, hh = blockIdx.x % H;
+  const int C = H * d;
+  for (int i = threadIdx.x; i < N * d; i += blockDim.x) {
+    const int r = i / d, c = i % d;
+    const float* row = qkv + static_cast<int64_t>(b * N + r) * 3 * C + hh * d + c;
+    sk[i] = row[C];
+    sv[i] = row[2 * C];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* p = sp + warp * N;
+  for (int qi = warp; qi < N; qi += 4) {
+    const float* q = qkv + static_cast<int64_t>(b * N + qi) * 3 * C + hh * d;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      float s = 0.f;
+      for (int c = 0; c < d; ++c) s = fmaf(q[c], sk[j * d + c], s);
+      s *= scale;
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < N; ++j) acc = fmaf(p[j], sv[j * d + c], acc);
+      out[static_cast<int64_t>(b * N + qi) * C + hh * d + c] = acc * inv;
+    }
+    __syncwarp();
+  }
+}
+
+inline unsigned grid_for(int64_t total, int threads = 256) {
+  int64_t g = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return static_cast<unsigned>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace iggt
+
+using namespace iggt;
+
+extern "C" int iggt_upsample_bilinear_nhwc(const void* x, void* out, int NB, int h, int w, int H, int W, int C,
+                                           const float* tabx, const float* taby, int dtype, iggt_stream_t stream) {
+  if (NB <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || (C % 16)) return -1;
+  if ((tabx == nullptr) != (taby == nullptr)) return -1;
+  const int64_t total = static_cast<int64_t>(NB) * H * W * (C / 8);
+  if (dtype) upsample_bilinear_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)x, (uint16_t*)out, NB, h, w, H, W, C, tabx, taby);
+  else upsample_bilinear_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)x, (uint16_t*)out, NB, h, w, H, W, C, tabx, taby);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int iggt_deconv_shuffle(const void* y, void* out, int NB, int h, int w, int C, int k, iggt_stream_t stream) {
+  if (NB <= 0 || (C % 8) || k <= 0) return -1;
+  const int64_t total = static_cast<int64_t>(NB) * h * w * k * k * (C / 8);
+  deconv_shuffle_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (uint4*)out, NB, h, w, C, k);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int iggt_im2col3x3_s2(const void* x, void* A, int NB, int h, int w, int C, iggt_stream_t stream) {
+  if (NB <= 0 || (C % 8)) return -1;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(NB) * ho * wo * 9 * (C / 8);
+  im2col_s2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)A, NB, h, w, C, ho, wo);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int iggt_dpt_tail(const void* x, const float* w, const float* b, float* out_main, float* out_conf,
+                             int NB, int H, int W, int OC, int mode, int dtype, iggt_stream_t stream) {
+  if (NB <= 0 || (OC != 2 && OC != 4 && OC != 8)) return -1;
+  if (mode != 2 && !out_conf) return -1;
+  const int64_t hw = static_cast<int64_t>(H) * W, npix = hw * NB;
+  cudaStream_t s = (cudaStream_t)stream;
+#define TAIL(BF, O) dpt_tail_kernel<BF, O><<<grid_for(npix), 256, 0, s>>>((const uint16_t*)x, w, b, out_main, out_conf, npix, hw, mode)
+  if (dtype) { if (OC == 2) TAIL(true, 2); else if (OC == 4) TAIL(true, 4); else TAIL(true, 8); }
+  else { if (OC == 2) TAIL(false, 2); else if (OC == 4) TAIL(false, 4); else TAIL(false, 8); }
+#undef TAIL
+  return (int)cudaGetLastError();
+}
+
+extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                                const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo,
+                                int M, int N, int K, int act, int dtype, iggt_stream_t stream) {
+  if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
+  const unsigned grid = (N + 7) / 8;
+  cudaStream_t s = (cudaStream_t)stream;
+#define SK(BF, MT) skinny_gemm_kernel<BF, MT><<<grid, 256, 0, s>>>(x, ldx, (const uint16_t*)W, ldw, bias, gamma, resid, ldr, out, ldo, M, N, K, act)
+  if (dtype) { if (M <= 8) SK(true, 8); else if (M <= 16) SK(true, 16); else SK(true, 32); }
+  else { if (M <= 8) SK(false, 8); else if (M <= 16) SK(false, 16); else SK(false, 32); }
+#undef SK
+  return (int)cudaGetLastError();
+}
+
+extern "C" int iggt_small_attention(const float* qkv, float* out, int B, int N, int H, int d, float scale,
+                                    iggt_stream_t stream) {
+  if (B <= 0 || N <= 0 || N > 256 || H <= 0 || d <= 0) return -1;
+  const size_t smem = (2 * static_cast<size_t>(N) * d + 4 * N) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  small_attention_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>(qkv, out, N, H, d, scale);
+  return (int)cudaGetLastError();
+}

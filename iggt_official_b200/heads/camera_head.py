@@ -1,0 +1,119 @@
+"""B200-native camera head: iterative pose refinement on the S camera tokens
+(reference: iggt/heads/camera_head.py:83-154, iggt/heads/head_act.py:12-35).
+
+M = B*S rows of width 2048 against 216 M parameters: every Linear is weight-bandwidth bound, so they run
+on the weight-streaming `iggt_skinny_gemm` (fp32 activations, 16-bit weights, fp32 accumulate) and the
+S x S attention on `iggt_small_attention`; LayerNorms use `iggt_layernorm` (fp32 out).  The AdaLN modulate
+(a few [B*S, 2048] elementwise ops) is expressed with torch tensor arithmetic.
+"""
+from typing import List
+
+import torch
+
+from .. import ops
+from ..layout import Node
+
+DIM = 2048
+HEADS = 16
+
+
+def _f32(p, device):
+    return p.detach().to(device, torch.float32).contiguous()
+
+
+class CameraHead(Node):
+    def __init__(self):
+        super().__init__()
+        self._pk = None
+        self._pk_key = None
+
+    def invalidate(self):
+        self._pk = None
+
+    def _packed(self, dtype, device):
+        key = (dtype, str(device))
+        if self._pk is not None and self._pk_key == key:
+            return self._pk
+        h16 = lambda p: p.detach().to(device=device, dtype=dtype).contiguous()
+        pk = {}
+        for i in range(4):
+            b = self.trunk._modules[str(i)]
+            pk[f"t{i}"] = dict(
+                n1w=_f32(b.norm1.weight, device), n1b=_f32(b.norm1.bias, device),
+                qkv_w=h16(b.attn.qkv.weight), qkv_b=_f32(b.attn.qkv.bias, device),
+                proj_w=h16(b.attn.proj.weight), proj_b=_f32(b.attn.proj.bias, device), ls1=_f32(b.ls1.gamma, device),
+                n2w=_f32(b.norm2.weight, device), n2b=_f32(b.norm2.bias, device),
+                fc1_w=h16(b.mlp.fc1.weight), fc1_b=_f32(b.mlp.fc1.bias, device),
+                fc2_w=h16(b.mlp.fc2.weight), fc2_b=_f32(b.mlp.fc2.bias, device), ls2=_f32(b.ls2.gamma, device))
+        pk["tok_w"], pk["tok_b"] = _f32(self.token_norm.weight, device), _f32(self.token_norm.bias, device)
+        pk["trk_w"], pk["trk_b"] = _f32(self.trunk_norm.weight, device), _f32(self.trunk_norm.bias, device)
+        ew = torch.zeros(DIM, 16, device=device, dtype=dtype)       # K = 9 padded to 16 for 16-byte rows
+        ew[:, :9] = self.embed_pose.weight.detach().to(device, dtype)
+        pk["emb_w"], pk["emb_b"] = ew, _f32(self.embed_pose.bias, device)
+        mod = self.poseLN_modulation._modules["1"]
+        pk["mod_w"], pk["mod_b"] = h16(mod.weight), _f32(mod.bias, device)
+        pk["pb1_w"], pk["pb1_b"] = h16(self.pose_branch.fc1.weight), _f32(self.pose_branch.fc1.bias, device)
+        pk["pb2_w"], pk["pb2_b"] = h16(self.pose_branch.fc2.weight), _f32(self.pose_branch.fc2.bias, device)
+        pk["empty"] = _f32(self.empty_pose_tokens, device).reshape(1, 9)
+        self._pk, self._pk_key = pk, key
+        return pk
+
+    @staticmethod
+    def _rows(fn, x, *a, **k):
+        """skinny GEMM handles <= 32 rows per launch; larger B*S go in row chunks."""
+        if x.shape[0] <= 32:
+            return fn(x, *a, **k)
+        outs = []
+        for r in range(0, x.shape[0], 32):
+            kk = dict(k)
+            if kk.get("resid") is not None:
+                kk["resid"] = kk["resid"][r:r + 32]
+            outs.append(fn(x[r:r + 32], *a, **kk))
+        return torch.cat(outs, 0)
+
+    def _block(self, x, w, B, S):
+        M = x.shape[0]
+        h = torch.empty_like(x)
+        ops.layernorm(x, w["n1w"], w["n1b"], 1e-5, h)
+        qkv = self._rows(ops.skinny_gemm, h, w["qkv_w"], w["qkv_b"])
+        o = ops.small_attention(qkv, B, S, HEADS, DIM // HEADS)
+        x = self._rows(ops.skinny_gemm, o, w["proj_w"], w["proj_b"], gamma=w["ls1"], resid=x)
+        ops.layernorm(x, w["n2w"], w["n2b"], 1e-5, h)
+        f = self._rows(ops.skinny_gemm, h, w["fc1_w"], w["fc1_b"], act=1)
+        return self._rows(ops.skinny_gemm, f, w["fc2_w"], w["fc2_b"], gamma=w["ls2"], resid=x)
+
+    @torch.no_grad()
+    def forward(self, aggregated_tokens_list: List[torch.Tensor], num_iterations: int = 4, compute_dtype=None,
+                camera_tokens: torch.Tensor = None) -> List[torch.Tensor]:
+        """`camera_tokens` [B,S,2048] (already gathered over ranks) overrides tokens_list[-1][:, :, 0]."""
+        if camera_tokens is None:
+            tok = aggregated_tokens_list[-1]
+            camera_tokens = tok[:, :, 0]
+        B, S, C = camera_tokens.shape
+        dev = camera_tokens.device
+        dt = compute_dtype or (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16)
+        pk = self._packed(dt, dev)
+        M = B * S
+        raw = camera_tokens.reshape(M, C).float().contiguous()
+        pt = torch.empty_like(raw)
+        ops.layernorm(raw, pk["tok_w"], pk["tok_b"], 1e-5, pt)
+        ptn = torch.empty_like(raw)
+        ops.layernorm(pt, None, None, 1e-6, ptn)                      # adaln_norm (no affine, eps 1e-6)
+        pred = None
+        outs = []
+        for _ in range(num_iterations):
+            inp = torch.zeros((M, 16), dtype=torch.float32, device=dev)
+            inp[:, :9] = pk["empty"] if pred is None else pred
+            e = self._rows(ops.skinny_gemm, inp, pk["emb_w"], pk["emb_b"], act=4)          # SiLU(embed_pose(.))
+            mod = self._rows(ops.skinny_gemm, e, pk["mod_w"], pk["mod_b"])
+            shift, scale, gate = mod[:, :DIM], mod[:, DIM:2 * DIM], mod[:, 2 * DIM:]
+            x = (gate * (ptn * (1 + scale) + shift) + pt).contiguous()
+            for i in range(4):
+                x = self._block(x, pk[f"t{i}"], B, S)
+            xn = torch.empty_like(x)
+            ops.layernorm(x, pk["trk_w"], pk["trk_b"], 1e-5, xn)
+            hdn = self._rows(ops.skinny_gemm, xn, pk["pb1_w"], pk["pb1_b"], act=1)
+            d = self._rows(ops.skinny_gemm, hdn, pk["pb2_w"], pk["pb2_b"])
+            pred = d if pred is None else pred + d
+            outs.append(torch.cat([pred[:, :7], torch.relu(pred[:, 7:])], -1).view(B, S, 9))
+        return outs

@@ -1,0 +1,105 @@
+"""Drop-in model classes: `IGGT` and `VGGT` with the reference constructor, `forward(images,
+query_points=None)` signature, output dictionary and `state_dict` layout (iggt/models/vggt.py:14-230),
+running on the sm_100a kernels of this package.
+
+    from iggt_official_b200.models.vggt import IGGT      # instead of iggt.models.vggt
+    model = IGGT(); model.load_state_dict(ckpt, strict=False); model.eval().to("cuda")
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.float16):
+        predictions = model(images)                       # [S,3,H,W] or [B,S,3,H,W] in [0,1]
+
+Differences from the reference that a caller can observe:
+  * CUDA only (no CPU fallback); the 16-bit compute dtype follows the enclosing autocast (fp16 when there is
+    none -- the reference would run fp32).
+  * S > 12 views works (the reference's frame-chunk path raises TypeError).
+  * `track_head` parameters are kept for checkpoint round-trip; passing `query_points` raises
+    NotImplementedError (out of scope).
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ..heads.camera_head import CameraHead
+from ..heads.dpt_head import DPTHead
+from ..layout import Node, load_layout, populate
+from .aggregator import Aggregator
+
+try:  # the reference mixes this in for from_pretrained / save_pretrained (vggt.py:4,132)
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+
+class _Base(nn.Module, PyTorchModelHubMixin):
+    _with_part = False
+
+    def __init__(self, img_size=518, patch_size=14, embed_dim=1024, only_train_adaptor=False):
+        super().__init__()
+        entries = load_layout(img_size, patch_size, embed_dim)
+        self.aggregator = Aggregator()
+        self.camera_head = CameraHead()
+        self.point_head = DPTHead(output_dim=4, activation="inv_log", use_point_feat=self._with_part)
+        self.depth_head = DPTHead(output_dim=2, activation="exp", use_point_feat=False)
+        self.track_head = Node()
+        if self._with_part:
+            from ..heads.part_head import PartAdaptor, PartHead
+            self.part_adaptor = PartAdaptor()
+            self.part_head = PartHead()
+        for name, mod in self.named_children():
+            populate(mod, entries, name + ".")
+        self.compute_dtype: Optional[torch.dtype] = None     # None: follow autocast, else fp16
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+
+    def invalidate_packed(self):
+        for m in self.modules():
+            if m is not self and hasattr(m, "invalidate"):
+                m.invalidate()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.invalidate_packed()
+        return out
+
+    def _dtype(self):
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor, query_points: torch.Tensor = None):
+        if len(images.shape) == 4:
+            images = images.unsqueeze(0)
+        if query_points is not None:
+            raise NotImplementedError("track_head (query_points) is outside the B200 hot path; "
+                                      "use the reference TrackHead on the returned tokens")
+        dt = self._dtype()
+        tokens, psi = self.aggregator(images, compute_dtype=dt)
+        predictions = {}
+        predictions["pose_enc"] = self.camera_head(tokens, compute_dtype=dt)
+        depth, depth_conf = self.depth_head(tokens, images=images, patch_start_idx=psi, compute_dtype=dt)
+        predictions["depth"] = depth
+        predictions["depth_conf"] = depth_conf
+        if self._with_part:
+            pts, pconf, point_feat = self.point_head(tokens, images=images, patch_start_idx=psi, compute_dtype=dt)
+        else:
+            pts, pconf = self.point_head(tokens, images=images, patch_start_idx=psi, compute_dtype=dt)
+        predictions["world_points"] = pts
+        predictions["world_points_conf"] = pconf
+        if self._with_part:
+            maps = self.part_adaptor(tokens, images=images, patch_start_idx=psi, compute_dtype=dt)
+            predictions["part_feat"] = self.part_head(maps, point_feature=point_feat, images=images,
+                                                      patch_start_idx=psi, compute_dtype=dt)
+        predictions["images"] = images
+        return predictions
+
+
+class VGGT(_Base):
+    """Reference `VGGT` (iggt/models/vggt.py:14-95): IGGT minus the part path. Its state_dict is the IGGT
+    layout without `part_adaptor.*` / `part_head.*`."""
+    _with_part = False
+
+
+class IGGT(_Base):
+    """Reference `IGGT` (iggt/models/vggt.py:132-230)."""
+    _with_part = True

@@ -58,14 +58,15 @@ def gemm_store32(a, w, bias=None, act=0, out=None):
     return out
 
 
-def gemm_resid32(a, w, x, bias=None, gamma=None):
+def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
     """x32[M,N] += gamma * (a @ w.T + bias), in place."""
     _chk2d(a); _chk2d(w); _chk2d(x)
     assert x.dtype == torch.float32
     M, K = a.shape
     N = w.shape[0]
     st = _lib.load().iggt_gemm_resid32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(),
-                                       x.stride(0), M, N, K, _dt(a), _ptr(bias), _ptr(gamma), _stream())
+                                       x.stride(0), M, N, K, _dt(a), _ptr(bias), _ptr(gamma),
+                                       1 if round_out16 else 0, _stream())
     _lib.check(st, "iggt_gemm_resid32")
     return x
 
@@ -84,7 +85,7 @@ def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b
     return out
 
 
-def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None):
+def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None, act_post=0):
     """x: [NB,H,W,Cin] 16-bit NHWC contiguous; wp: [Cout, taps*Cin] tap-major packed."""
     assert x.is_cuda and x.dim() == 4 and x.is_contiguous()
     NB, H, W, Cin = x.shape
@@ -95,7 +96,7 @@ def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None):
     if resid is not None:
         assert resid.shape == out.shape and resid.is_contiguous()
     st = _lib.load().iggt_conv_nhwc(x.data_ptr(), wp.data_ptr(), out.data_ptr(), NB, H, W, Cin, Cout, taps,
-                                    _dt(x), _ptr(bias), act, _ptr(resid), _stream())
+                                    _dt(x), _ptr(bias), act, _ptr(resid), _ptr(resid2), act_post, _stream())
     _lib.check(st, "iggt_conv_nhwc")
     return out
 
@@ -155,3 +156,69 @@ def special_tokens(cam, reg, x, NI, T, R, C, S_loc, view_offset):
                                          view_offset, _stream())
     _lib.check(st, "iggt_special_tokens")
     return x
+
+
+def upsample_bilinear(x, H, W, tabx=None, taby=None, out=None):
+    """[NB,h,w,C] 16-bit NHWC -> [NB,H,W,C], align_corners=True (+ optional split pos-embed tables)."""
+    assert x.is_cuda and x.dim() == 4 and x.is_contiguous()
+    NB, h, w, C = x.shape
+    if out is None:
+        out = torch.empty((NB, H, W, C), dtype=x.dtype, device=x.device)
+    st = _lib.load().iggt_upsample_bilinear_nhwc(x.data_ptr(), out.data_ptr(), NB, h, w, H, W, C, _ptr(tabx),
+                                                 _ptr(taby), _dt(x), _stream())
+    _lib.check(st, "iggt_upsample_bilinear_nhwc")
+    return out
+
+
+def deconv_shuffle(y, NB, h, w, C, k):
+    out = torch.empty((NB, h * k, w * k, C), dtype=y.dtype, device=y.device)
+    st = _lib.load().iggt_deconv_shuffle(y.data_ptr(), out.data_ptr(), NB, h, w, C, k, _stream())
+    _lib.check(st, "iggt_deconv_shuffle")
+    return out
+
+
+def im2col3x3_s2(x):
+    NB, h, w, C = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    A = torch.empty((NB * ho * wo, 9 * C), dtype=x.dtype, device=x.device)
+    st = _lib.load().iggt_im2col3x3_s2(x.data_ptr(), A.data_ptr(), NB, h, w, C, _stream())
+    _lib.check(st, "iggt_im2col3x3_s2")
+    return A, ho, wo
+
+
+def dpt_tail(x, w, b, mode):
+    """x [NB,H,W,32] 16-bit -> (main, conf) fp32; mode 0 depth, 1 points, 2 part (channels-first, conf None)."""
+    NB, H, W, _ = x.shape
+    OC = w.shape[0]
+    if mode == 2:
+        main = torch.empty((NB, OC, H, W), dtype=torch.float32, device=x.device)
+        conf = None
+    else:
+        main = torch.empty((NB, H, W, OC - 1), dtype=torch.float32, device=x.device)
+        conf = torch.empty((NB, H, W), dtype=torch.float32, device=x.device)
+    st = _lib.load().iggt_dpt_tail(x.data_ptr(), w.data_ptr(), b.data_ptr(), main.data_ptr(), _ptr(conf), NB, H, W,
+                                   OC, mode, _dt(x), _stream())
+    _lib.check(st, "iggt_dpt_tail")
+    return main, conf
+
+
+def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
+    """fp32 x [M<=32, K] times 16-bit w [N, K]^T -> fp32 [M, N]."""
+    _chk2d(x); _chk2d(w)
+    assert x.dtype == torch.float32
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    st = _lib.load().iggt_skinny_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(gamma),
+                                      _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(),
+                                      out.stride(0), M, N, K, act, _dt(w), _stream())
+    _lib.check(st, "iggt_skinny_gemm")
+    return out
+
+
+def small_attention(qkv, B, N, H, d):
+    out = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
+    st = _lib.load().iggt_small_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _stream())
+    _lib.check(st, "iggt_small_attention")
+    return out

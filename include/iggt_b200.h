@@ -34,12 +34,13 @@ int iggt_gemm_store16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
                       int M, int N, int K, int dtype, const float* bias, int act,
                       const void* addend, int add_rows, int64_t add_ld, iggt_stream_t stream);
 
-/* x32[M,N] += gamma * (A W^T + bias)   (fp32 residual stream, TMA reduce-add).
+/* x32[M,N] += gamma * r(A W^T + bias)   (fp32 residual stream, TMA reduce-add); r() rounds to the 16-bit
+ * dtype when round_out16 != 0 (what an autocast nn.Linear returns before LayerScale), identity otherwise.
  * Replaces attn.proj / mlp.fc2 + LayerScale + residual (iggt/layers/attention.py:74-75, mlp.py:38,
  * layer_scale.py:27, block.py:105-106). */
 int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx,
                       int M, int N, int K, int dtype, const float* bias, const float* gamma,
-                      iggt_stream_t stream);
+                      int round_out16, iggt_stream_t stream);
 
 /* out32[M,N] = act(A W^T + bias) (fp32 output). */
 int iggt_gemm_store32(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo,
@@ -56,12 +57,13 @@ int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   iggt_stream_t stream);
 
 /* 3x3 (pad 1, stride 1) or 1x1 convolution as implicit GEMM over an NHWC 16-bit tensor:
- * out[NB,H,W,Cout] = act(conv(x[NB,H,W,Cin], Wp[Cout, taps*Cin]) + bias) (+ resid[NB,H,W,Cout]).
+ * out[NB,H,W,Cout] = act_post(act(conv(x[NB,H,W,Cin], Wp[Cout, taps*Cin]) + bias) + resid + resid2)
+ * (resid / resid2: optional [NB,H,W,Cout] 16-bit tensors; act codes as above).
  * Wp is packed tap-major: k = (ky*3+kx)*Cin + ci.  Cin % 64 == 0.
  * Replaces the Conv2d layers of iggt/heads/dpt_head.py:298-316,369-411. */
 int iggt_conv_nhwc(const void* x, const void* Wp, void* out, int NB, int H, int W, int Cin, int Cout,
                    int taps, int dtype, const float* bias, int act, const void* resid,
-                   iggt_stream_t stream);
+                   const void* resid2, int act_post, iggt_stream_t stream);
 
 
 /* ---- Flash attention forward (tcgen05 QK^T / PV, TMEM accumulators, online softmax), head_dim 64.
@@ -97,6 +99,40 @@ int iggt_dino_assemble(const void* pe16, const float* cls, const float* reg, con
  * Replaces iggt/models/aggregator.py:230-234,338-361. */
 int iggt_special_tokens(const float* cam, const float* reg, float* x, int NI, int T, int R, int C,
                         int S_loc, int view_offset, iggt_stream_t stream);
+
+/* ---- Dense-head / camera-head kernels (NHWC 16-bit activations). */
+
+/* F.interpolate(bilinear, align_corners=True) [NB,h,w,C] -> [NB,H,W,C], optionally + the UV sinusoid
+ * pos-embed split as tabx[W][C/2] (first half of the channels) and taby[H][C/2] (second half), both fp32.
+ * Replaces iggt/heads/dpt_head.py:251-259,478 (+ :274-284). */
+int iggt_upsample_bilinear_nhwc(const void* x, void* out, int NB, int h, int w, int H, int W, int C,
+                                const float* tabx, const float* taby, int dtype, iggt_stream_t stream);
+
+/* ConvTranspose2d with kernel == stride k: y[(n,yy,xx), (dy*k+dx)*C+co] -> out[n, k*yy+dy, k*xx+dx, co].
+ * Replaces the scatter half of iggt/heads/dpt_head.py:85-92 (the GEMM half is iggt_gemm_store16). */
+int iggt_deconv_shuffle(const void* y, void* out, int NB, int h, int w, int C, int k, iggt_stream_t stream);
+
+/* im2col of a 3x3 / stride 2 / pad 1 conv: [NB,h,w,C] -> [NB*ho*wo, 9*C], k = tap*C + c.
+ * Replaces the gather half of iggt/heads/dpt_head.py:94-97. */
+int iggt_im2col3x3_s2(const void* x, void* A, int NB, int h, int w, int C, iggt_stream_t stream);
+
+/* Per-pixel 1x1 conv 32 -> OC (fp32 weights w[OC][32], b[OC]) + head activation on x[NB,H,W,32].
+ * mode 0 (depth): main[NB,H,W,OC-1] = exp, conf[NB,H,W] = 1+exp;  mode 1 (points): sign*expm1|.|;
+ * mode 2 (part_feat): raw, channels-first main[NB,OC,H,W].
+ * Replaces iggt/heads/dpt_head.py:264-265 + iggt/heads/head_act.py:61-125, part_head.py:240-243. */
+int iggt_dpt_tail(const void* x, const float* w, const float* b, float* out_main, float* out_conf, int NB,
+                  int H, int W, int OC, int mode, int dtype, iggt_stream_t stream);
+
+/* out[M,N] = resid + gamma * act(x[M,K] W[N,K]^T + bias), M <= 32, fp32 activations, 16-bit weights
+ * (weight-bandwidth bound; act: 0 none, 1 GELU, 2 ReLU, 4 SiLU).  Camera-head Linear layers,
+ * iggt/heads/camera_head.py:83-154. */
+int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                     const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo, int M,
+                     int N, int K, int act, int dtype, iggt_stream_t stream);
+
+/* fp32 softmax attention for tiny sequences: qkv[B*N, 3*H*d] -> out[B*N, H*d] (camera tokens). */
+int iggt_small_attention(const float* qkv, float* out, int B, int N, int H, int d, float scale,
+                         iggt_stream_t stream);
 
 #ifdef __cplusplus
 }

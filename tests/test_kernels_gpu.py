@@ -233,3 +233,100 @@ def test_patchify_and_assemble(ops, dtype):
     y4 = y.view(2, NI, T, C)
     assert torch.equal(y4[:, 0, 0], cam[0].expand(2, C)) and torch.equal(y4[:, 1, 0], cam[1].expand(2, C))
     assert torch.equal(y4[:, 0, 1:1 + R], regt[0].expand(2, R, C)) and torch.equal(y4[:, 1, 1:1 + R], regt[1].expand(2, R, C))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("with_pe", [False, True])
+def test_upsample_bilinear(ops, dtype, with_pe):
+    g = torch.Generator(device="cuda").manual_seed(17)
+    NB, h, w, H, W, C = 2, 19, 23, 37, 41, 128
+    x = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+    tx = torch.randn(W, C // 2, device="cuda", generator=g) if with_pe else None
+    ty = torch.randn(H, C // 2, device="cuda", generator=g) if with_pe else None
+    out = ops.upsample_bilinear(x, H, W, tx, ty)
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    if with_pe:
+        ref = ref + torch.cat([tx[None, None].expand(NB, H, W, C // 2), ty[None, :, None].expand(NB, H, W, C // 2)], -1)
+    assert _relmax(out, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k", [2, 4])
+def test_deconv_as_gemm_plus_shuffle(ops, dtype, k):
+    from iggt_official_b200.heads.dpt_head import pack_deconv
+    g = torch.Generator(device="cuda").manual_seed(19)
+    NB, h, w, C = 2, 5, 7, 64
+    x = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+    wt = (torch.randn(C, C, k, k, device="cuda", generator=g) / 8).to(dtype)
+    b = torch.randn(C, device="cuda", generator=g)
+    wp, bp = pack_deconv(wt, b, dtype, "cuda")
+    y = ops.gemm_store16(x.view(-1, C), wp, bp)
+    out = ops.deconv_shuffle(y, NB, h, w, C, k)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=k).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_stride2_conv_as_im2col_gemm(ops, dtype):
+    from iggt_official_b200.heads.dpt_head import pack_conv3x3
+    g = torch.Generator(device="cuda").manual_seed(23)
+    for h, w in [(37, 37), (6, 8)]:
+        NB, C = 2, 64
+        x = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+        wt = (torch.randn(128, C, 3, 3, device="cuda", generator=g) / 24).to(dtype)
+        b = torch.randn(128, device="cuda", generator=g)
+        A, ho, wo = ops.im2col3x3_s2(x)
+        out = ops.gemm_store16(A, pack_conv3x3(wt, dtype, "cuda"), b).view(NB, ho, wo, 128)
+        torch.cuda.synchronize()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+        assert out.shape == ref.shape and _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("oc,mode", [(2, 0), (4, 1), (8, 2)])
+def test_dpt_tail(ops, dtype, oc, mode):
+    g = torch.Generator(device="cuda").manual_seed(29)
+    NB, H, W = 2, 9, 11
+    x = torch.randn(NB, H, W, 32, device="cuda", generator=g).to(dtype)
+    w = torch.randn(oc, 32, device="cuda", generator=g) / 6
+    b = torch.randn(oc, device="cuda", generator=g) * 0.1
+    main, conf = ops.dpt_tail(x, w, b, mode)
+    torch.cuda.synchronize()
+    o = x.float() @ w.t() + b
+    if mode == 2:
+        assert conf is None and _relmax(main, o.permute(0, 3, 1, 2)) < 1e-5
+    else:
+        xyz = o[..., :-1]
+        ref = torch.exp(xyz) if mode == 0 else torch.sign(xyz) * torch.expm1(xyz.abs())
+        assert ((main - ref).abs() / ref.abs().clamp_min(1e-3)).max().item() < 1e-4   # fp32 exp/expm1
+        assert ((conf - (1 + o[..., -1].exp())).abs() / (1 + o[..., -1].exp())).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K,act", [(8, 2048, 2048, 0), (3, 9, 1024, 0), (20, 6144, 16, 4), (32, 1024, 8192, 1)])
+def test_skinny_gemm(ops, dtype, M, N, K, act):
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    b = torch.randn(N, device="cuda", generator=g)
+    gam = torch.rand(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    out = ops.skinny_gemm(x, w, b, act=act, gamma=gam, resid=res)
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t() + b
+    ref = {0: lambda t: t, 1: F.gelu, 4: F.silu}[act](ref)
+    ref = res + gam * ref
+    assert _relmax(out, ref.float()) < 2e-5       # fp32 activations, exact 16-bit weights: fp32 noise only
+
+
+def test_small_attention(ops):
+    g = torch.Generator(device="cuda").manual_seed(37)
+    B, N, H, d = 2, 13, 16, 128
+    qkv = torch.randn(B * N, 3 * H * d, device="cuda", generator=g)
+    out = ops.small_attention(qkv, B, N, H, d)
+    torch.cuda.synchronize()
+    q, k, v = qkv.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).transpose(1, 2).reshape(B * N, H * d)
+    assert _relmax(out, ref) < 1e-5
