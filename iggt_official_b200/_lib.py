@@ -45,6 +45,14 @@ SIGNATURES = {
     "iggt_skinny_gemm": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                          c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "iggt_small_attention": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "iggt_layernorm16": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p],
+    "iggt_col2im_k4s2p1": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "iggt_ocab_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_void_p],
+    "iggt_window_attention": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "iggt_channel_mean": [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
+    "iggt_se_scale_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_int64, c_int, c_int, c_float, c_int, c_void_p],
     "iggt_special_tokens": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 

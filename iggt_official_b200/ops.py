@@ -30,6 +30,31 @@ def _chk2d(t):
     assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1, "expect a CUDA row-major 2-D tensor"
 
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# Launch accounting: every C-ABI launch goes through _call().  STATS counts launches (bench.py reports
+# them as `gpu_launches`); when TRACE is a list, each launch is bracketed by CUDA events on the launching
+# stream together with its algorithmic FLOPs / bytes (bench.py's roofline numbers).
+STATS = {"launches": 0}
+TRACE = None
+
+
+def _call(name, flops, nbytes, *args):
+    fn = getattr(_lib.load(), name)
+    STATS["launches"] += 1
+    if TRACE is None:
+        st = fn(*args)
+    else:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args)
+        e1.record()
+        TRACE.append((name, float(flops), float(nbytes), e0, e1))
+    _lib.check(st, name)
+
+
 def gemm_store16(a, w, bias=None, act=0, addend=None, add_rows=0, out=None):
     """out16[M,N] = act(a @ w.T + bias) (+ addend[row % add_rows])."""
     _chk2d(a); _chk2d(w)
@@ -38,11 +63,11 @@ def gemm_store16(a, w, bias=None, act=0, addend=None, add_rows=0, out=None):
     if out is None:
         out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     _chk2d(out)
-    st = _lib.load().iggt_gemm_store16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+    _call("iggt_gemm_store16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N),
+          a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                        out.stride(0), M, N, K, _dt(a), _ptr(bias), act, _ptr(addend),
                                        add_rows if addend is not None else 0,
                                        addend.stride(0) if addend is not None else 0, _stream())
-    _lib.check(st, "iggt_gemm_store16")
     return out
 
 
@@ -52,9 +77,9 @@ def gemm_store32(a, w, bias=None, act=0, out=None):
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    st = _lib.load().iggt_gemm_store32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+    _call("iggt_gemm_store32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N,
+          a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                        out.stride(0), M, N, K, _dt(a), _ptr(bias), act, _stream())
-    _lib.check(st, "iggt_gemm_store32")
     return out
 
 
@@ -64,10 +89,10 @@ def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
     assert x.dtype == torch.float32
     M, K = a.shape
     N = w.shape[0]
-    st = _lib.load().iggt_gemm_resid32(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(),
+    _call("iggt_gemm_resid32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 8.0 * M * N,
+          a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(),
                                        x.stride(0), M, N, K, _dt(a), _ptr(bias), _ptr(gamma),
                                        1 if round_out16 else 0, _stream())
-    _lib.check(st, "iggt_gemm_resid32")
     return x
 
 
@@ -77,11 +102,11 @@ def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b
     M, K = a.shape
     if out is None:
         out = torch.empty((M, 3 * C), dtype=a.dtype, device=a.device)
-    st = _lib.load().iggt_gemm_qkv(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+    _call("iggt_gemm_qkv", 6.0 * M * C * K, 2.0 * (M * K + 3 * C * K + 3 * M * C),
+          a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, C, K, _dt(a), _ptr(bias), 1 if qk_norm else 0,
                                    _ptr(qn_w), _ptr(qn_b), _ptr(kn_w), _ptr(kn_b), _ptr(rope_cos),
                                    _ptr(rope_sin), _ptr(pos_yx), T, _stream())
-    _lib.check(st, "iggt_gemm_qkv")
     return out
 
 
@@ -95,9 +120,9 @@ def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None
         out = torch.empty((NB, H, W, Cout), dtype=x.dtype, device=x.device)
     if resid is not None:
         assert resid.shape == out.shape and resid.is_contiguous()
-    st = _lib.load().iggt_conv_nhwc(x.data_ptr(), wp.data_ptr(), out.data_ptr(), NB, H, W, Cin, Cout, taps,
+    _call("iggt_conv_nhwc", 2.0 * NB * H * W * Cout * taps * Cin, 2.0 * (NB * H * W * (Cin + Cout) + Cout * taps * Cin),
+          x.data_ptr(), wp.data_ptr(), out.data_ptr(), NB, H, W, Cin, Cout, taps,
                                     _dt(x), _ptr(bias), act, _ptr(resid), _ptr(resid2), act_post, _stream())
-    _lib.check(st, "iggt_conv_nhwc")
     return out
 
 
@@ -107,10 +132,10 @@ def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None):
         _chk2d(t)
     if out is None:
         out = torch.empty((num_seq * Lq, H * 64), dtype=q.dtype, device=q.device)
-    st = _lib.load().iggt_attention_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+    _call("iggt_attention_fwd", 4.0 * num_seq * Lq * Lk * H * 64, 2.0 * num_seq * H * 64 * (2 * Lq + 2 * Lk),
+          q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
                                         v.stride(0), out.data_ptr(), out.stride(0), num_seq, Lq, Lk, H, 64,
                                         float(scale), _dt(q), _stream())
-    _lib.check(st, "iggt_attention_fwd")
     return out
 
 
@@ -127,10 +152,10 @@ def layernorm(x, w, b, eps, out, groups=None, rows_out=None, rows_in=None, in_of
         groups, rows_out, rows_in = 1, x.shape[0], x.shape[0]
     if out_rows_per_group is None:
         out_rows_per_group = rows_out
-    st = _lib.load().iggt_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), C, _ptr(w),
+    _call("iggt_layernorm", 0, groups * rows_out * C * (4 + out.element_size()),
+          x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), C, _ptr(w),
                                     _ptr(b), float(eps), groups, rows_out, rows_in, in_off,
                                     out_rows_per_group, out_off, _KIND[out.dtype], _stream())
-    _lib.check(st, "iggt_layernorm")
     return out
 
 
@@ -139,22 +164,22 @@ def patchify(images, KP, dtype):
     assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
     NI, _, H, W = images.shape
     A = torch.empty((NI * (H // 14) * (W // 14), KP), dtype=dtype, device=images.device)
-    st = _lib.load().iggt_patchify(images.data_ptr(), A.data_ptr(), NI, H, W, KP, _KIND[dtype], _stream())
-    _lib.check(st, "iggt_patchify")
+    _call("iggt_patchify", 0, images.numel() * 4 + A.numel() * 2,
+          images.data_ptr(), A.data_ptr(), NI, H, W, KP, _KIND[dtype], _stream())
     return A
 
 
 def dino_assemble(pe16, cls, reg, pos, x, NI, P, R, C):
-    st = _lib.load().iggt_dino_assemble(pe16.data_ptr(), cls.data_ptr(), reg.data_ptr(), pos.data_ptr(),
+    _call("iggt_dino_assemble", 0, x.numel() * 4 + pe16.numel() * 2,
+          pe16.data_ptr(), cls.data_ptr(), reg.data_ptr(), pos.data_ptr(),
                                         x.data_ptr(), NI, P, R, C, _dt(pe16), _stream())
-    _lib.check(st, "iggt_dino_assemble")
     return x
 
 
 def special_tokens(cam, reg, x, NI, T, R, C, S_loc, view_offset):
-    st = _lib.load().iggt_special_tokens(cam.data_ptr(), reg.data_ptr(), x.data_ptr(), NI, T, R, C, S_loc,
+    _call("iggt_special_tokens", 0, NI * (1 + R) * C * 4,
+          cam.data_ptr(), reg.data_ptr(), x.data_ptr(), NI, T, R, C, S_loc,
                                          view_offset, _stream())
-    _lib.check(st, "iggt_special_tokens")
     return x
 
 
@@ -164,16 +189,16 @@ def upsample_bilinear(x, H, W, tabx=None, taby=None, out=None):
     NB, h, w, C = x.shape
     if out is None:
         out = torch.empty((NB, H, W, C), dtype=x.dtype, device=x.device)
-    st = _lib.load().iggt_upsample_bilinear_nhwc(x.data_ptr(), out.data_ptr(), NB, h, w, H, W, C, _ptr(tabx),
+    _call("iggt_upsample_bilinear_nhwc", 0, 2.0 * (x.numel() + out.numel()),
+          x.data_ptr(), out.data_ptr(), NB, h, w, H, W, C, _ptr(tabx),
                                                  _ptr(taby), _dt(x), _stream())
-    _lib.check(st, "iggt_upsample_bilinear_nhwc")
     return out
 
 
 def deconv_shuffle(y, NB, h, w, C, k):
     out = torch.empty((NB, h * k, w * k, C), dtype=y.dtype, device=y.device)
-    st = _lib.load().iggt_deconv_shuffle(y.data_ptr(), out.data_ptr(), NB, h, w, C, k, _stream())
-    _lib.check(st, "iggt_deconv_shuffle")
+    _call("iggt_deconv_shuffle", 0, 4.0 * y.numel(),
+          y.data_ptr(), out.data_ptr(), NB, h, w, C, k, _stream())
     return out
 
 
@@ -181,8 +206,8 @@ def im2col3x3_s2(x):
     NB, h, w, C = x.shape
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     A = torch.empty((NB * ho * wo, 9 * C), dtype=x.dtype, device=x.device)
-    st = _lib.load().iggt_im2col3x3_s2(x.data_ptr(), A.data_ptr(), NB, h, w, C, _stream())
-    _lib.check(st, "iggt_im2col3x3_s2")
+    _call("iggt_im2col3x3_s2", 0, 2.0 * (x.numel() + A.numel()),
+          x.data_ptr(), A.data_ptr(), NB, h, w, C, _stream())
     return A, ho, wo
 
 
@@ -196,9 +221,9 @@ def dpt_tail(x, w, b, mode):
     else:
         main = torch.empty((NB, H, W, OC - 1), dtype=torch.float32, device=x.device)
         conf = torch.empty((NB, H, W), dtype=torch.float32, device=x.device)
-    st = _lib.load().iggt_dpt_tail(x.data_ptr(), w.data_ptr(), b.data_ptr(), main.data_ptr(), _ptr(conf), NB, H, W,
+    _call("iggt_dpt_tail", 2.0 * NB * H * W * 32 * OC, NB * H * W * (64 + 4 * OC),
+          x.data_ptr(), w.data_ptr(), b.data_ptr(), main.data_ptr(), _ptr(conf), NB, H, W,
                                    OC, mode, _dt(x), _stream())
-    _lib.check(st, "iggt_dpt_tail")
     return main, conf
 
 
@@ -210,15 +235,72 @@ def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    st = _lib.load().iggt_skinny_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(gamma),
+    _call("iggt_skinny_gemm", 2.0 * M * N * K, 2.0 * N * K + 4.0 * M * (K + N),
+          x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(gamma),
                                       _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(),
                                       out.stride(0), M, N, K, act, _dt(w), _stream())
-    _lib.check(st, "iggt_skinny_gemm")
     return out
 
 
 def small_attention(qkv, B, N, H, d):
     out = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
-    st = _lib.load().iggt_small_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _stream())
-    _lib.check(st, "iggt_small_attention")
+    _call("iggt_small_attention", 4.0 * B * N * N * H * d, 16.0 * B * N * H * d,
+          qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _stream())
+    return out
+
+
+def layernorm16(x, w, b, eps=1e-5, out=None):
+    """LayerNorm over the last dim (64 / 128 / 256) of a contiguous 16-bit tensor."""
+    assert x.is_cuda and x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    _call("iggt_layernorm16", 0, 4.0 * x.numel(), x.data_ptr(), out.data_ptr(), rows, C, w.data_ptr(), b.data_ptr(),
+          float(eps), _dt(x), _stream())
+    return out
+
+
+def col2im_k4s2p1(y, bias, NB, h, w, C):
+    out = torch.empty((NB, 2 * h, 2 * w, C), dtype=y.dtype, device=y.device)
+    _call("iggt_col2im_k4s2p1", 0, 2.0 * (y.numel() + out.numel()), y.data_ptr(), bias.data_ptr(), out.data_ptr(),
+          NB, h, w, C, _dt(y), _stream())
+    return out
+
+
+def ocab_attention(q, k, v, table, rpi):
+    """q, k, v: [NB,h,w,256] contiguous 16-bit; table [361,4] fp32; rpi [64,144] int32 in [0,361)."""
+    NB, h, w, C = q.shape
+    assert C == 256 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    out = torch.empty_like(q)
+    _call("iggt_ocab_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 144 * 64, 8.0 * q.numel(),
+          q.data_ptr(), k.data_ptr(), v.data_ptr(), table.data_ptr(), rpi.data_ptr(), out.data_ptr(), NB, h, w,
+          _dt(q), _stream())
+    return out
+
+
+def window_attention(qkv):
+    """qkv [NB,h,w,384] contiguous 16-bit -> [NB,h,w,128]."""
+    NB, h, w, C3 = qkv.shape
+    assert C3 == 384 and qkv.is_contiguous()
+    out = torch.empty((NB, h, w, 128), dtype=qkv.dtype, device=qkv.device)
+    _call("iggt_window_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 64 * 32, 2.0 * (qkv.numel() + out.numel()),
+          qkv.data_ptr(), out.data_ptr(), NB, h, w, _dt(qkv), _stream())
+    return out
+
+
+def channel_mean(x):
+    """x [NB,h,w,C] 16-bit -> [NB,C] fp32 spatial means."""
+    NB, h, w, C = x.shape
+    mean = torch.empty((NB, C), dtype=torch.float32, device=x.device)
+    _call("iggt_channel_mean", 0, 2.0 * x.numel(), x.data_ptr(), mean.data_ptr(), NB, h * w, C, _dt(x), _stream())
+    return mean
+
+
+def se_scale_add(y0, cx, mean, w1, b1, w2, b2, alpha):
+    NB, h, w, C = y0.shape
+    out = torch.empty_like(y0)
+    _call("iggt_se_scale_add", 0, 6.0 * y0.numel(), y0.data_ptr(), cx.data_ptr(), mean.data_ptr(), w1.data_ptr(),
+          b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), NB, h * w, C, w1.shape[0], float(alpha),
+          _dt(y0), _stream())
     return out

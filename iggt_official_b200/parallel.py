@@ -1,0 +1,76 @@
+"""View sharding over the GPUs of one box (new design -- the reference is single-GPU).
+
+Rank r holds views [r*S_loc, (r+1)*S_loc) of every scene.  DINOv2, frame blocks and every dense head are
+per-view, so they need no communication; each of the 24 global blocks needs the K and V of all views:
+one NCCL all-gather of the rank's K|V rows ([B*S_loc*T, 2048] 16-bit) per global block, after which the
+local queries attend to the full key set with the same flash kernel (exact softmax).  The camera head needs
+the S camera tokens of layer 23 (one tiny all-gather).
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def make_kv_gather(group, world: int, B: int, S_loc: int, T: int):
+    """Returns f(qkv[M_loc, 3072]) -> (K view, V view, Lk) over all ranks' tokens, scene-major."""
+    M_loc = B * S_loc * T
+
+    def gather(qkv: torch.Tensor):
+        dev, dt = qkv.device, qkv.dtype
+        send = qkv[:, 1024:].contiguous()                                  # [M_loc, 2048]  (K | V)
+        recv = torch.empty((world, M_loc, 2048), dtype=dt, device=dev)
+        dist.all_gather_into_tensor(recv.view(world * M_loc, 2048), send, group=group)
+        if B > 1:  # rows arrive (rank, scene, view, token); attention wants (scene, rank, view, token)
+            recv = recv.view(world, B, S_loc * T, 2048).transpose(0, 1).contiguous()
+        kv = recv.view(world * M_loc, 2048)
+        return kv[:, :1024], kv[:, 1024:], world * S_loc * T
+
+    return gather
+
+
+def gather_camera_tokens(tokens23: torch.Tensor, group, world: int) -> torch.Tensor:
+    """tokens23 [B, S_loc, T, 2048] (local) -> camera tokens [B, S, 2048] of all views."""
+    cam = tokens23[:, :, 0].contiguous()                                   # [B, S_loc, 2048]
+    if world == 1:
+        return cam
+    B, S_loc, C = cam.shape
+    recv = torch.empty((world, B, S_loc, C), dtype=cam.dtype, device=cam.device)
+    dist.all_gather_into_tensor(recv.view(-1), cam.view(-1), group=group)
+    return recv.permute(1, 0, 2, 3).reshape(B, world * S_loc, C).contiguous()
+
+
+def shard_views(model, group=None):
+    """Configure `model` (IGGT / VGGT) for view-sharded execution over `group` (default: WORLD)."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    group = group if group is not None else dist.group.WORLD
+    model.aggregator.process_group = group
+    model._shard_group = group
+    return model
+
+
+@torch.no_grad()
+def forward_sharded(model, images_local: torch.Tensor, rank: int, world: int, group=None):
+    """images_local [B, S_loc, 3, H, W]: this rank's views.  Returns the prediction dict for the local
+    views (pose_enc covers all S views, identical on every rank)."""
+    group = group if group is not None else dist.group.WORLD
+    model.aggregator.process_group = group if world > 1 else None
+    if images_local.dim() == 4:
+        images_local = images_local.unsqueeze(0)
+    B, S_loc = images_local.shape[:2]
+    dt = model._dtype()
+    tokens, psi = model.aggregator(images_local, compute_dtype=dt, view_offset=rank * S_loc,
+                                   total_views=world * S_loc)
+    cam = gather_camera_tokens(tokens[23], group, world)
+    pred = {"pose_enc": model.camera_head(tokens, compute_dtype=dt, camera_tokens=cam)}
+    d, dc = model.depth_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
+    out = model.point_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
+    pred["depth"], pred["depth_conf"] = d, dc
+    pred["world_points"], pred["world_points_conf"] = out[0], out[1]
+    if getattr(model, "_with_part", False) and getattr(model, "part_enabled", True):
+        maps = model.part_adaptor(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
+        pred["part_feat"] = model.part_head(maps, point_feature=out[2], images=images_local, patch_start_idx=psi,
+                                            compute_dtype=dt)
+    pred["images"] = images_local
+    return pred

@@ -134,6 +134,37 @@ int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int64_t ldw, co
 int iggt_small_attention(const float* qkv, float* out, int B, int N, int H, int d, float scale,
                          iggt_stream_t stream);
 
+/* ---- Part (instance-feature) path kernels. */
+
+/* LayerNorm (affine) over C in {64,128,256} channels of 16-bit rows -> 16-bit.
+ * Replaces nn.LayerNorm in iggt/heads/window_sa.py (patch_embed.norm, norm1, norm2, norm). */
+int iggt_layernorm16(const void* x, void* y, int64_t rows, int C, const float* w, const float* b, float eps,
+                     int dtype, iggt_stream_t stream);
+
+/* ConvTranspose2d(k4,s2,p1) gather: Y[(n,iy,ix), (ky*4+kx)*C+co] (GEMM output) -> out[NB,2h,2w,C] + bias.
+ * Replaces the scatter half of iggt/heads/adaptor.py:152-157. */
+int iggt_col2im_k4s2p1(const void* Y, const float* bias, void* out, int NB, int h, int w, int C, int dtype,
+                       iggt_stream_t stream);
+
+/* OCAB window cross-attention on projected q,k,v [NB,h,w,256] (4 heads x 64; 8x8 query windows gathered with
+ * the reference's scrambled partition, 12x12 zero-padded key windows, bias table[361][4] indexed by
+ * rpi[64][144] (already wrapped to [0,361)).  Replaces iggt/heads/window_sa.py:280-314. */
+int iggt_ocab_attention(const void* q, const void* k, const void* v, const float* table, const int* rpi,
+                        void* out, int NB, int h, int w, int dtype, iggt_stream_t stream);
+
+/* HAB 8x8 window self-attention on qkv [NB,h,w,384] (4 heads x 32) -> [NB,h,w,128].
+ * Replaces iggt/heads/window_sa.py:214-219 + iggt/heads/block.py:113-130. */
+int iggt_window_attention(const void* qkv, void* out, int NB, int h, int w, int dtype, iggt_stream_t stream);
+
+/* Per-image channel means of x[NB,hw,C] -> mean[NB,C] fp32 (AdaptiveAvgPool2d(1), window_sa.py:29). */
+int iggt_channel_mean(const void* x, float* mean, int NB, int64_t hw, int C, int dtype, iggt_stream_t stream);
+
+/* y = y0 + alpha * cx * sigmoid(W2 relu(W1 mean + b1) + b2)   (ChannelAttention + HAB combine,
+ * iggt/heads/window_sa.py:26-38,225); w1 [R,C], w2 [C,R]. */
+int iggt_se_scale_add(const void* y0, const void* cx, const float* mean, const float* w1, const float* b1,
+                      const float* w2, const float* b2, void* y, int NB, int64_t hw, int C, int R, float alpha,
+                      int dtype, iggt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

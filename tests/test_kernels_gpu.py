@@ -330,3 +330,96 @@ def test_small_attention(ops):
     q, k, v = qkv.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).transpose(1, 2).reshape(B * N, H * d)
     assert _relmax(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------ part-path kernels (csrc/part.cu)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_layernorm16(ops, dtype, C):
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = (torch.randn(3, 5, 7, C, device="cuda", generator=g) * 2 + 0.5).to(dtype)
+    w = torch.rand(C, device="cuda", generator=g) + 0.5
+    b = torch.randn(C, device="cuda", generator=g)
+    out = ops.layernorm16(x, w, b)
+    torch.cuda.synchronize()
+    assert _relmax(out, F.layer_norm(x.float(), (C,), w, b, 1e-5)) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_deconv_k4s2p1_as_gemm_plus_col2im(ops, dtype):
+    g = torch.Generator(device="cuda").manual_seed(43)
+    NB, h, w, C = 2, 5, 6, 64
+    x = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+    wt = (torch.randn(C, C, 4, 4, device="cuda", generator=g) / 16).to(dtype)
+    b = torch.randn(C, device="cuda", generator=g)
+    wp = wt.permute(2, 3, 1, 0).reshape(16 * C, C).contiguous()
+    y = ops.gemm_store16(x.view(-1, C), wp, None)
+    out = ops.col2im_k4s2p1(y, b, NB, h, w, C)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and _relmax(out, ref) < 3 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ocab_attention_matches_oracle_window_math(ops, dtype):
+    """The kernel against the oracle's restatement of OCAB's partition / unfold / bias (oracle.ref_model._ocab
+    internals), including the scrambled query windows."""
+    from oracle import ref_model
+    g = torch.Generator(device="cuda").manual_seed(47)
+    b, h, w, c, ws, heads = 2, 16, 24, 256, 8, 4
+    q = torch.randn(b, h, w, c, device="cuda", generator=g).to(dtype)
+    k = torch.randn(b, h, w, c, device="cuda", generator=g).to(dtype)
+    v = torch.randn(b, h, w, c, device="cuda", generator=g).to(dtype)
+    table = torch.randn(361, heads, device="cuda", generator=g) * 0.5
+    rpi = ref_model.calculate_rpi_oca(8).cuda()
+    out = ops.ocab_attention(q, k, v, table, (rpi % 361).int().contiguous())
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().permute(0, 3, 1, 2) for t in (q, k, v))
+    q_win = ref_model.window_partition(qf, ws).view(-1, ws * ws, c)
+    kvw = F.unfold(torch.cat([kf, vf], 1), kernel_size=(12, 12), stride=ws, padding=2)
+    nw = kvw.shape[-1]
+    kvw = kvw.view(b, 2, c, 144, nw).permute(1, 0, 4, 3, 2).reshape(2, b * nw, 144, c)
+    d = c // heads
+    qh = q_win.reshape(-1, 64, heads, d).permute(0, 2, 1, 3) * d ** -0.5
+    kh = kvw[0].reshape(-1, 144, heads, d).permute(0, 2, 1, 3)
+    vh = kvw[1].reshape(-1, 144, heads, d).permute(0, 2, 1, 3)
+    bias = table[rpi.view(-1)].view(64, 144, -1).permute(2, 0, 1)
+    att = torch.softmax(qh @ kh.transpose(-2, -1) + bias.unsqueeze(0), -1)
+    o = (att @ vh).transpose(1, 2).reshape(-1, 64, c).view(-1, ws, ws, c)
+    ref = ref_model.window_reverse(o, ws, h, w)
+    assert _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_window_attention(ops, dtype):
+    from oracle import ref_model
+    g = torch.Generator(device="cuda").manual_seed(53)
+    b, h, w, c, heads = 2, 16, 8, 128, 4
+    qkv = torch.randn(b, h, w, 3 * c, device="cuda", generator=g).to(dtype)
+    out = ops.window_attention(qkv)
+    torch.cuda.synchronize()
+    xw = ref_model.window_partition(qkv.float(), 8).view(-1, 64, 3, heads, c // heads).transpose(1, 3)
+    q, k, v = xw[:, :, 0], xw[:, :, 1], xw[:, :, 2]
+    o = (torch.softmax(q @ k.transpose(-2, -1) * (c // heads) ** -0.5, -1) @ v).transpose(1, 2).reshape(-1, 64, c)
+    ref = ref_model.window_reverse(o.view(-1, 8, 8, c), 8, h, w)
+    assert _relmax(out, ref) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_channel_attention_pieces(ops, dtype):
+    g = torch.Generator(device="cuda").manual_seed(59)
+    NB, h, w, C, R = 3, 24, 16, 128, 4
+    y0 = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+    cx = torch.randn(NB, h, w, C, device="cuda", generator=g).to(dtype)
+    w1 = torch.randn(R, C, device="cuda", generator=g) / 8
+    b1 = torch.randn(R, device="cuda", generator=g)
+    w2 = torch.randn(C, R, device="cuda", generator=g)
+    b2 = torch.randn(C, device="cuda", generator=g)
+    mean = ops.channel_mean(cx)
+    out = ops.se_scale_add(y0, cx, mean, w1, b1, w2, b2, 0.01)
+    torch.cuda.synchronize()
+    m = cx.float().mean((1, 2))
+    assert _relmax(mean, m) < 1e-4
+    s = torch.sigmoid(F.relu(m @ w1.t() + b1) @ w2.t() + b2)
+    ref = y0.float() + 0.01 * cx.float() * s[:, None, None, :]
+    assert _relmax(out, ref) < _tol(dtype)
