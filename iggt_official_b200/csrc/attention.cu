@@ -281,9 +281,9 @@ int launch_attention(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
 
 using namespace iggt;
 
-extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                  int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk,
-                                  int H, int head_dim, float scale, int dtype, iggt_stream_t stream) {
+extern "C" int iggt_attention_fwd_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                     int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk,
+                                     int H, int head_dim, float scale, int dtype, iggt_stream_t stream) {
   if (head_dim != 64) return -1;
   if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return -1;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -2;

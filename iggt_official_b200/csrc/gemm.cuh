@@ -81,15 +81,18 @@ __device__ __forceinline__ float round16(float x) {
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 1) return gelu_erf(x);
+  if (act == 1) return gelu_fast(x);
   if (act == 2) return fmaxf(x, 0.0f);
   if (act == 3) return x > 0.0f ? x : 0.01f * x;
   return x;
 }
 
 // CONV: A operand comes from a 4-D NHWC tensor map (box {64, TW, TH, 1}); otherwise 2-D [M,K].
-template <int BN, int EPI, bool BF16, bool CONV>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// G = epilogue warpgroups (1 or 2). With G = 2 the column chunks of a tile alternate between two 4-warp
+// groups (each TMEM lane quarter is then read by two warps), doubling epilogue issue slots and halving
+// the registers available per thread (384 threads) -- used for every epilogue except the qkv one.
+template <int BN, int EPI, bool BF16, bool CONV, int G>
+__global__ void __launch_bounds__(128 + 128 * G, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using SM = GemmSmem<BN>;
@@ -122,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * G);
     }
     fence_barrier_init();
   }
@@ -198,9 +201,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (128 threads, 1 row each)
-    const int ew = warp - 4;               // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int grp = (warp - 4) >> 2;       // epilogue group
+    const int ew = (warp - 4) & 3;         // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     const int row = ew * 32 + lane;        // row inside the tile
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (ew == 0 && lane == 0);
+    constexpr int NBUF = 2 / G;            // staging buffers per group
+    uint8_t* const stg_grp = staging + grp * NBUF * SM::STG_BYTES;
+    const uint32_t bar_id = 1 + grp;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_count = 0;
@@ -227,13 +234,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
       if constexpr (EPI == EPI_STORE16 || EPI == EPI_QKV) {
+        const int nvalid = min(BN / 64, (p.N - n0 + 63) / 64);
+        if (grp >= nvalid) {               // nothing to read for this group: release immediately
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
 #pragma unroll 1
-        for (int c64 = 0; c64 < BN / 64; ++c64) {
+        for (int c64 = grp; c64 < nvalid; c64 += G) {
           const int col0 = n0 + c64 * 64;
-          if (col0 >= p.N) break;
-          uint8_t* stg = staging + (store_count & 1) * SM::STG_BYTES;
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
+          uint8_t* stg = stg_grp + (store_count % NBUF) * SM::STG_BYTES;
+          if (leader) tma_store_wait_read<NBUF - 1>();
+          named_bar_sync(bar_id, 128);
           float v[64];
           {
             uint32_t r0[32], r1[32];
@@ -243,8 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
           }
-          if (c64 == BN / 64 - 1 || col0 + 64 >= p.N) {
-            // last TMEM read of this tile: release the accumulator stage
+          if (c64 + G >= nvalid) {
+            // last TMEM read of this tile by this warp: release the accumulator stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -295,7 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.act == 1) {
               // autocast: GELU is evaluated on the 16-bit Linear output (iggt/layers/mlp.py:35-36)
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = gelu_erf(round16<BF16>(v[i]));
+              for (int i = 0; i < 64; ++i) v[i] = gelu_fast(round16<BF16>(v[i]));
             } else if (p.act) {
 #pragma unroll
               for (int i = 0; i < 64; ++i) v[i] = apply_act(v[i], p.act);
@@ -353,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<uint4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (leader) {
             if constexpr (CONV) tma_store_4d(&tmC, stg, col0, x0, y0, img);
             else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
@@ -363,17 +375,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       } else {
         // fp32 outputs: 32 columns (128 B) per staging tile
+        const int nvalid = min(BN / 32, (p.N - n0 + 31) / 32);
+        if (grp >= nvalid) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
 #pragma unroll 1
-        for (int c32 = 0; c32 < BN / 32; ++c32) {
+        for (int c32 = grp; c32 < nvalid; c32 += G) {
           const int col0 = n0 + c32 * 32;
-          if (col0 >= p.N) break;
-          uint8_t* stg = staging + (store_count & 1) * SM::STG_BYTES;
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
+          uint8_t* stg = stg_grp + (store_count % NBUF) * SM::STG_BYTES;
+          if (leader) tma_store_wait_read<NBUF - 1>();
+          named_bar_sync(bar_id, 128);
           uint32_t r0[32];
           tmem_ld_32x32(t_row + c32 * 32, r0);
           tmem_ld_wait();
-          if (c32 == BN / 32 - 1 || col0 + 32 >= p.N) {
+          if (c32 + G >= nvalid) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -412,7 +429,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<float4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (leader) {
             if constexpr (EPI == EPI_RESID32) tma_reduce_add_2d(&tmC, stg, col0, mt * GEMM_BM);
             else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);

@@ -31,10 +31,10 @@ inline int choose_bn(int m_tiles, int N) {
   return (c128 * 100 < c256 * 92) ? 128 : 256;
 }
 
-template <int BN, int EPI, bool BF16, bool CONV>
+template <int BN, int EPI, bool BF16, bool CONV, int G = (EPI == EPI_QKV ? 1 : 2)>
 inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                               const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, EPI, BF16, CONV>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, BF16, CONV, G>;
   static bool configured = false;
   constexpr int smem = GemmSmem<BN>::TOTAL;
   if (!configured) {
@@ -45,7 +45,7 @@ inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, cons
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   if (grid <= 0) return 0;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tA, tB, tC, p);
+  kern<<<grid, 128 + 128 * G, smem, stream>>>(tA, tB, tC, p);
   return (int)cudaGetLastError();
 }
 

@@ -156,53 +156,81 @@ dpt_tail_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, con
   }
 }
 
-// out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 32 rows, fp32
-// activations, 16-bit weights streamed once (one warp per output column).  Camera head Linear layers
-// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.
-template <bool BF16, int MT>
+// out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 8 rows per launch
+// (the host loops over row chunks), fp32 activations, 16-bit weights streamed once.  Camera-head Linear layers
+// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.  CTA = 8 warps x 4 output
+// columns; the activation K-chunk lives in shared memory and each lane keeps its 8 x 8 slice in registers
+// across the 4 columns, so shared-memory traffic is 1/4 of the weight traffic's FMA demand.
+constexpr int SK_KC = 1024;   // K chunk staged in smem (8 rows x 1024 fp32 = 32 KB)
+constexpr int SK_NC = 4;      // columns per warp
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ W, int64_t ldw,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* resid,
                    int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int act) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (n >= N) return;
-  const int lane = threadIdx.x & 31;
-  float acc[MT];
+  __shared__ __align__(16) float sx[8 * SK_KC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * SK_NC;
+  float acc[SK_NC][8];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-  const uint16_t* wr = W + static_cast<int64_t>(n) * ldw;
-  for (int k = lane * 8; k < K; k += 256) {
-    float wf[8];
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(wr + k)), wf);
+  for (int c = 0; c < SK_NC; ++c)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k + 4));
-        acc[m] += a.x * wf[0] + a.y * wf[1] + a.z * wf[2] + a.w * wf[3] + b.x * wf[4] + b.y * wf[5] +
-                  b.z * wf[6] + b.w * wf[7];
+    for (int m = 0; m < 8; ++m) acc[c][m] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    const int kc = min(SK_KC, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x * 4; i < 8 * kc; i += 256 * 4) {
+      const int m = i / kc, kk = i % kc;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) v = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k0 + kk));
+      *reinterpret_cast<float4*>(sx + m * kc + kk) = v;
+    }
+    __syncthreads();
+    for (int k = lane * 8; k < kc; k += 256) {
+      float xr[8][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(sx + m * kc + k);
+        const float4 b = *reinterpret_cast<const float4*>(sx + m * kc + k + 4);
+        xr[m][0] = a.x; xr[m][1] = a.y; xr[m][2] = a.z; xr[m][3] = a.w;
+        xr[m][4] = b.x; xr[m][5] = b.y; xr[m][6] = b.z; xr[m][7] = b.w;
+      }
+#pragma unroll
+      for (int c = 0; c < SK_NC; ++c) {
+        if (n0 + c < N) {
+          float wf[8];
+          unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(W + static_cast<int64_t>(n0 + c) * ldw + k0 + k)), wf);
+#pragma unroll
+          for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][m] = fmaf(xr[m][j], wf[j], acc[c][m]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int m = 0; m < MT; ++m) {
+  for (int c = 0; c < SK_NC; ++c)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
-  }
-  if (lane == 0) {
-    const float bb = bias ? bias[n] : 0.f;
-    const float g = gamma ? gamma[n] : 1.f;
+    for (int m = 0; m < 8; ++m) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) {
-        float v = acc[m] + bb;
-        if (act == 1) v = gelu_erf(v);
-        else if (act == 2) v = fmaxf(v, 0.f);
-        else if (act == 4) v = v / (1.0f + expf(-v));  // SiLU
-        v *= g;
-        if (resid) v += resid[m * ldr + n];
-        out[m * ldo + n] = v;
-      }
+      for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
+    }
+  if (lane < SK_NC * 8) {
+    const int c = lane / 8, m = lane % 8;
+    const int n = n0 + c;
+    if (n < N && m < M) {
+      float v = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < SK_NC; ++cc)
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) if (cc == c && mm == m) v = acc[cc][mm];
+      v += bias ? bias[n] : 0.f;
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 4) v = v / (1.0f + expf(-v));  // SiLU
+      v *= gamma ? gamma[n] : 1.f;
+      if (resid) v += resid[m * ldr + n];
+      out[m * ldo + n] = v;
     }
   }
 }
@@ -307,12 +335,15 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
                                 const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo,
                                 int M, int N, int K, int act, int dtype, iggt_stream_t stream) {
   if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
-  const unsigned grid = (N + 7) / 8;
+  if (K > SK_KC && (K % SK_KC)) return -1;
+  const unsigned grid = (N + 8 * SK_NC - 1) / (8 * SK_NC);
   cudaStream_t s = (cudaStream_t)stream;
-#define SK(BF, MT) skinny_gemm_kernel<BF, MT><<<grid, 256, 0, s>>>(x, ldx, (const uint16_t*)W, ldw, bias, gamma, resid, ldr, out, ldo, M, N, K, act)
-  if (dtype) { if (M <= 8) SK(true, 8); else if (M <= 16) SK(true, 16); else SK(true, 32); }
-  else { if (M <= 8) SK(false, 8); else if (M <= 16) SK(false, 16); else SK(false, 32); }
-#undef SK
+  for (int m0 = 0; m0 < M; m0 += 8) {   // weights of the later chunks come from L2
+    const int mm = M - m0 < 8 ? M - m0 : 8;
+    const float* rp = resid ? resid + m0 * ldr : nullptr;
+    if (dtype) skinny_gemm_kernel<true><<<grid, 256, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    else skinny_gemm_kernel<false><<<grid, 256, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -78,6 +78,11 @@ def main():
     oc = torch.empty(8, 148, 148, 256, device=dev, dtype=dt)
     ms = timeit(lambda: ops.conv_nhwc(xc, wc, None, act=2, out=oc), flush=flush)
     res["conv3x3_148"] = {"ms": ms, "tflops": 2.0 * 8 * 148 * 148 * 256 * 2304 / ms / 1e9}
+    # camera-head skinny GEMM (M = 8 camera tokens): weight streaming
+    xs = torch.randn(8, 2048, device=dev)
+    ws = (torch.randn(6144, 2048, device=dev) / 45).to(dt)
+    ms = timeit(lambda: ops.skinny_gemm(xs, ws), flush=flush)
+    res["skinny_8x6144x2048"] = {"ms": ms, "gbs": ws.numel() * 2 / ms / 1e6}
     print(json.dumps(res, indent=1))
 
 
