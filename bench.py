@@ -171,9 +171,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
         out = step(images_dev)
     barrier()
+    if args.quick:
+        for _ in range(args.steps):
+            out = step(images_dev)
+        barrier()
+        if rank == 0:
+            print(json.dumps({"quick": True, "launches_per_step": ops.STATS["launches"] // (args.warmup + args.steps)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
@@ -312,6 +321,7 @@ def main():
     ap.add_argument("--part", action="store_true", help="IGGT with the part path (needs an even patch grid, e.g. --size 532)")
     ap.add_argument("--ref-views", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling mode: warm-up + steps only (run this under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -172,26 +172,25 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (++kst == A2_STAGES) { kst = 0; kph ^= 1; }
         }
         for (int j = 0; j < n_kv; ++j) {
-          const bool more = (j + 1 < n_kv);
-          mbar_wait(&v_full[vst], vph);
-          const uint32_t v_addr = smem_u32(sV + vst * A2_TILE);
-          uint32_t k_addr = 0;
-          if (more) {
+          // S(j+1) for both tiles is issued as soon as the softmax warpgroups have pulled S(j) into registers
+          // (s_empty), i.e. long before they finish tile j: the softmax never waits for the tensor pipe.
+          if (j + 1 < n_kv) {
             mbar_wait(&k_full[kst], kph);
-            k_addr = smem_u32(sK + kst * A2_TILE);
-          }
-          issue_pv(0, v_addr);
-          if (more) issue_qk(0, k_addr); else umma_commit(&q_empty[0]);
-          issue_pv(1, v_addr);
-          umma_commit(&v_empty[vst]);
-          if (++vst == A2_STAGES) { vst = 0; vph ^= 1; }
-          if (more) {
+            const uint32_t k_addr = smem_u32(sK + kst * A2_TILE);
+            issue_qk(0, k_addr);
             issue_qk(1, k_addr);
             umma_commit(&k_empty[kst]);
             if (++kst == A2_STAGES) { kst = 0; kph ^= 1; }
           } else {
+            umma_commit(&q_empty[0]);
             umma_commit(&q_empty[1]);
           }
+          mbar_wait(&v_full[vst], vph);
+          const uint32_t v_addr = smem_u32(sV + vst * A2_TILE);
+          issue_pv(0, v_addr);
+          issue_pv(1, v_addr);
+          umma_commit(&v_empty[vst]);
+          if (++vst == A2_STAGES) { vst = 0; vph ^= 1; }
         }
       }
     }
@@ -238,13 +237,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         float s[A2_BK];
         {
-          uint32_t r[32];
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld_32x32(tS, r0);
+          tmem_ld_32x32(tS + 32, r1);
+          tmem_ld_32x32(tS + 64, r2);
+          tmem_ld_32x32(tS + 96, r3);
+          tmem_ld_wait();
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            tmem_ld_32x32(tS + ch * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s[ch * 32 + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) {
+            s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]);
+            s[64 + i] = __uint_as_float(r2[i]); s[96 + i] = __uint_as_float(r3[i]);
           }
         }
         tc_fence_before();
@@ -263,15 +265,19 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const float m_new = fmaxf(m, fmaxf(mx0, mx1));
         const float alpha = ex2_approx((m - m_new) * c);
         const float mc = m_new * c;
-        float sum0 = 0.f, sum1 = 0.f;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < A2_BK; i += 2) {
+        for (int i = 0; i < A2_BK; i += 4) {
           s[i] = ex2_approx(fmaf(s[i], c, -mc));
           s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
+          s[i + 2] = ex2_approx(fmaf(s[i + 2], c, -mc));
+          s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
           sum0 += s[i];
           sum1 += s[i + 1];
+          sum2 += s[i + 2];
+          sum3 += s[i + 3];
         }
-        l = fmaf(l, alpha, sum0 + sum1);
+        l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));
         m = m_new;
         mbar_wait(&p_empty[t], (kv_cnt & 1) ^ 1);
 #pragma unroll

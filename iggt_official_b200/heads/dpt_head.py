@@ -193,7 +193,7 @@ class DPTHead(Node):
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, aggregated_tokens_list: List[torch.Tensor], images: torch.Tensor, patch_start_idx: int,
-                frames_chunk_size: int = 4, compute_dtype=None):
+                frames_chunk_size: int = 8, compute_dtype=None):
         B, S, _, H, W = images.shape
         dev = images.device
         dt = compute_dtype or (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16)
