@@ -66,7 +66,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 16384;                 // 128 rows x 128 B staging tile
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int VEC_BYTES = BN * 4 + (BN * 4 > 1024 ? BN * 4 : 1024);   // bias[BN] + (gamma[BN] | q/k-norm vectors [4][64])
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STG_BYTES + 256 /*barriers*/ + VEC_BYTES;
 };
 
 template <bool BF16>
@@ -97,8 +98,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using SM = GemmSmem<BN>;
   constexpr int STAGES = SM::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * SM::A_BYTES;
   uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;
@@ -108,6 +109,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,6 +210,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int NBUF = 2 / G;            // staging buffers per group
     uint8_t* const stg_grp = staging + grp * NBUF * SM::STG_BYTES;
     const uint32_t bar_id = 1 + grp;
+    const int gtid = ew * 32 + lane;       // thread index inside the group
+    float* const vb = epi_vec;                  // this tile's bias   [BN]  (staged before the accumulator is ready)
+    float* const vg = vb + BN;                  // this tile's gamma  [BN]  (EPI_RESID32)
+    float* const vn = vb + BN;                  // q_norm w,b | k_norm w,b  [4][64]  (EPI_QKV, BN >= 128)
+    if constexpr (EPI == EPI_QKV) {
+      if (p.qk_norm) {
+        for (int i = gtid; i < 64; i += 128) {
+          vn[i] = p.qn_w[i]; vn[64 + i] = p.qn_b[i]; vn[128 + i] = p.kn_w[i]; vn[192 + i] = p.kn_b[i];
+        }
+      }
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_count = 0;
@@ -229,6 +242,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         grow = (long)mt * GEMM_BM + row;
         if (grow >= p.M) grow = -1;
       }
+      // stage the tile's per-column vectors in smem while the MMAs of this tile are still running
+      // (with the smem carve-out this kernel uses there is no L1 left to cache them)
+      named_bar_sync(3, 128 * G);          // every epilogue thread is done with the previous tile's vectors
+      for (int i = grp * 128 + gtid; i < BN; i += 128 * G) {
+        const int col = n0 + i;
+        vb[i] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        if constexpr (EPI == EPI_RESID32) vg[i] = (p.gamma && col < p.N) ? __ldg(p.gamma + col) : 1.f;
+      }
+      named_bar_sync(3, 128 * G);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
@@ -261,20 +283,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          if (p.bias) {
+          {
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
-              if (col0 + i < p.N) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
+              const float4 b = *reinterpret_cast<const float4*>(vb + c64 * 64 + i);
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
           }
           if constexpr (EPI == EPI_QKV) {
             if (p.qk_norm && col0 < 2 * p.C) {
               const bool is_k = col0 >= p.C;
-              const float* nw = is_k ? p.kn_w : p.qn_w;
-              const float* nb = is_k ? p.kn_b : p.qn_b;
+              const float* nw = vn + (is_k ? 128 : 0);
+              const float* nb = nw + 64;
               // the reference rounds the Linear output to 16 bit before the fp32 LayerNorm (autocast)
               float s = 0.f;
 #pragma unroll
@@ -285,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; q += d * d; }
               const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f);
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(nw + i) + __ldg(nb + i);
+              for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * nw[i] + nb[i];
               // 2-D RoPE: dims [0,32) rotate with the y position, [32,64) with x; halves of 16
               const int t = (grow >= 0) ? static_cast<int>(grow % p.T) : 0;
               const int py = __ldg(p.pos_yx + 2 * t), px = __ldg(p.pos_yx + 2 * t + 1);
@@ -400,21 +420,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            if (col0 + i < p.N) {
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            const float4 b = *reinterpret_cast<const float4*>(vb + c32 * 32 + i);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            if constexpr (EPI == EPI_RESID32) {
+              if (p.round_out16) {
+                v[i] = round16<BF16>(v[i]); v[i + 1] = round16<BF16>(v[i + 1]);
+                v[i + 2] = round16<BF16>(v[i + 2]); v[i + 3] = round16<BF16>(v[i + 3]);
               }
-              if constexpr (EPI == EPI_RESID32) {
-                if (p.round_out16) {
-                  v[i] = round16<BF16>(v[i]); v[i + 1] = round16<BF16>(v[i + 1]);
-                  v[i + 2] = round16<BF16>(v[i + 2]); v[i + 3] = round16<BF16>(v[i + 3]);
-                }
-                if (p.gamma) {
-                  const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + i));
-                  v[i] *= g.x; v[i + 1] *= g.y; v[i + 2] *= g.z; v[i + 3] *= g.w;
-                }
-              }
+              const float4 g = *reinterpret_cast<const float4*>(vg + c32 * 32 + i);
+              v[i] *= g.x; v[i + 1] *= g.y; v[i + 2] *= g.z; v[i + 3] *= g.w;
             }
           }
           if constexpr (EPI == EPI_STORE32) {
