@@ -13,6 +13,7 @@
 // TMEM map (512 columns): S_A [0,128) S_B [128,256) PV_A0 [256,320) PV_A1 [320,384) PV_B0 [384,448) PV_B1 [448,512)
 //
 // Replaces F.scaled_dot_product_attention at iggt/layers/attention.py:61-66 (see include/iggt_b200.h).
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include "../../include/iggt_b200.h"
@@ -346,12 +347,16 @@ using namespace iggt;
 extern "C" int iggt_attention_fwd_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                      int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
                                      int head_dim, float scale, int dtype, iggt_stream_t stream);
+extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                     int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
+                                     int head_dim, float scale, int dtype, iggt_stream_t stream);
 
 extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                   int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
                                   int head_dim, float scale, int dtype, iggt_stream_t stream) {
-  static const bool use_v1 = (getenv("IGGT_ATTN_V1") != nullptr);
-  if (use_v1) return iggt_attention_fwd_v1(q, ldq, k, ldk, v, ldv, o, ldo, num_seq, Lq, Lk, H, head_dim, scale, dtype, stream);
+  static const int ver = [] { const char* e = getenv("IGGT_ATTN"); return e ? atoi(e) : 3; }();
+  if (ver == 1) return iggt_attention_fwd_v1(q, ldq, k, ldk, v, ldv, o, ldo, num_seq, Lq, Lk, H, head_dim, scale, dtype, stream);
+  if (ver == 3) return iggt_attention_fwd_v3(q, ldq, k, ldk, v, ldv, o, ldo, num_seq, Lq, Lk, H, head_dim, scale, dtype, stream);
   if (head_dim != 64) return -1;
   if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return -1;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -2;

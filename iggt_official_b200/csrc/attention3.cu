@@ -1,0 +1,403 @@
+// Flash-attention forward v3 for head_dim 64 on sm_100a.
+//
+// Persistent CTAs over (sequence, head, pair of 128-row query tiles), 20 warps:
+//   WG0     : warp 0 TMA producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator      (setmaxnreg.dec)
+//   WG1,WG2 : softmax of query tile A, each thread owns HALF a query row (64 of the 128 keys of a kv tile)
+//   WG3,WG4 : softmax of query tile B                                                       (setmaxnreg.inc)
+// Four softmax warps per SM sub-partition hide the mbarrier / TMEM / MUFU latencies that left v2 (two per
+// sub-partition) at 50 % of the MUFU roofline (profiles/r01_ncu_attention_v2.md).
+// O accumulates in TMEM across kv tiles (tcgen05.mma accumulate); the running max is only refreshed -- and O
+// rescaled in TMEM (tcgen05.ld / tcgen05.st) -- when some row's max grows by more than 2^8 (lazy rescaling), so
+// the steady-state loop is: TMEM->reg S, max, exp2, pack, st.shared P.  Row halves agree on the max through a
+// shared-memory exchange that only happens on a rescale; the decision is taken with one bar.red.or per tile.
+//
+// TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+#include <stdlib.h>
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include "../../include/iggt_b200.h"
+
+namespace iggt {
+
+constexpr int A3_BQ = 128;
+constexpr int A3_BK = 128;
+constexpr int A3_D = 64;
+constexpr int A3_STAGES = 3;
+constexpr int A3_THREADS = 640;
+constexpr int A3_TILE = A3_BK * A3_D * 2;     // 16 KB
+constexpr int A3_P = A3_BQ * A3_BK * 2;       // 32 KB
+constexpr int A3_XCHG = 2 * 2 * 128 * 4;      // max / sum exchange: [tile][half][row] fp32
+constexpr int A3_SMEM = A3_TILE * (2 + 2 * A3_STAGES) + 2 * A3_P + A3_XCHG + 512;
+constexpr float A3_TAU = 8.0f;                // lazy-rescale threshold in log2 units
+
+struct Attn3Params {
+  int Lq, Lk, H, num_seq;
+  int q_pairs;
+  int total_items;
+  int64_t ldo;
+  void* o;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// barrier + OR-reduction over `nthreads` threads of named barrier `id`
+__device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "bar.red.or.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"(pred ? 1u : 0u)
+      : "memory");
+  return out != 0;
+}
+
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-3
+// Chebyshev polynomial for 2^f (max relative error 1.0e-4, below half an fp16 ulp of P), exponent patched in
+// with an integer add.  Used for EMU of every 4 probabilities to take load off the 16-op/clk/SM MUFU unit.
+__device__ __forceinline__ float ex2_emulated(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23
+  const float f = x - (t - 12582912.0f);
+  float pz = fmaf(0.05583828315138817f, f, 0.2426394820213318f);
+  pz = fmaf(pz, f, 0.6931367516517639f);
+  pz = fmaf(pz, f, 0.9999245405197144f);
+  return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
+
+template <bool BF16, int EMU>
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * A3_TILE;
+  uint8_t* sV = sK + A3_STAGES * A3_TILE;
+  uint8_t* sP = sV + A3_STAGES * A3_TILE;
+  float* xchg = reinterpret_cast<float*>(sP + 2 * A3_P);         // [2 tiles][2 halves][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + A3_XCHG);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = q_full + 2;          // [2]
+  uint64_t* k_full = q_empty + 2;          // [3]
+  uint64_t* k_empty = k_full + A3_STAGES;
+  uint64_t* v_full = k_empty + A3_STAGES;
+  uint64_t* v_empty = v_full + A3_STAGES;
+  uint64_t* s_full = v_empty + A3_STAGES;  // [2]
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;          // [2]  committed after every PV
+  uint64_t* o_free = o_full + 2;           // [2]  final O of an item has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_kv = (p.Lk + A3_BK - 1) / A3_BK;
+
+  if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);   mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);   mbar_init(&s_empty[i], 256);
+      mbar_init(&p_full[i], 256); mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);   mbar_init(&o_free[i], 256);
+    }
+    for (int i = 0; i < A3_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int st = 0; uint32_t ph = 0;
+      uint32_t item_cnt = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
+        const int qp = item % p.q_pairs;
+        const int head = (item / p.q_pairs) % p.H;
+        const int seq = item / (p.q_pairs * p.H);
+        const int col = head * A3_D;
+        const uint32_t qpar = item_cnt & 1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[t], qpar ^ 1);
+          mbar_expect_tx(&q_full[t], A3_TILE);
+          tma_load_2d(sQ + t * A3_TILE, &tmQ, &q_full[t], col, seq * p.Lq + (qp * 2 + t) * A3_BQ);
+        }
+        for (int j = 0; j < n_kv; ++j) {
+          const int row = seq * p.Lk + j * A3_BK;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], A3_TILE);
+          tma_load_2d(sK + st * A3_TILE, &tmK, &k_full[st], col, row);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], A3_TILE);
+          tma_load_2d(sV + st * A3_TILE, &tmV, &v_full[st], col, row);
+          if (++st == A3_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_f16(A3_BQ, A3_BK, BF16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(A3_BQ, A3_D, BF16, false, true);   // V is MN-major
+      int kst = 0; uint32_t kph = 0;
+      int vst = 0; uint32_t vph = 0;
+      uint32_t qk_cnt = 0;            // QK issues per tile (same for both tiles)
+      uint32_t pv_cnt = 0;            // PV issues per tile
+      uint32_t item_cnt = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
+        const uint32_t qpar = item_cnt & 1;
+        mbar_wait(&q_full[0], qpar);
+        mbar_wait(&q_full[1], qpar);
+        for (int j = -1; j < n_kv; ++j) {
+          // S(j+1) of both tiles: as soon as the softmax warps have pulled S(j) into registers
+          if (j + 1 < n_kv) {
+            mbar_wait(&k_full[kst], kph);
+            const uint32_t k_addr = smem_u32(sK + kst * A3_TILE);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(&s_empty[t], (qk_cnt & 1) ^ 1);
+              tc_fence_after();
+              const uint32_t q_addr = smem_u32(sQ + t * A3_TILE);
+#pragma unroll
+              for (int kk = 0; kk < A3_D / 16; ++kk)
+                umma_f16(tmem_base + t * A3_BK, make_desc_sw128(q_addr + kk * 32, 1024),
+                         make_desc_sw128(k_addr + kk * 32, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+              umma_commit(&s_full[t]);
+            }
+            ++qk_cnt;
+            umma_commit(&k_empty[kst]);
+            if (++kst == A3_STAGES) { kst = 0; kph ^= 1; }
+          } else {
+            umma_commit(&q_empty[0]);
+            umma_commit(&q_empty[1]);
+          }
+          if (j < 0) continue;
+          // O += P(j) V(j) for both tiles
+          mbar_wait(&v_full[vst], vph);
+          const uint32_t v_addr = smem_u32(sV + vst * A3_TILE);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&p_full[t], pv_cnt & 1);
+            if (j == 0) mbar_wait(&o_free[t], qpar ^ 1);     // previous item's O has been read out
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sP + t * A3_P);
+            const uint32_t d_tmem = tmem_base + 256 + t * 64;
+#pragma unroll
+            for (int kk = 0; kk < A3_BK / 16; ++kk)
+              umma_f16(d_tmem, make_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 1024),
+                       make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
+            umma_commit(&o_full[t]);
+            umma_commit(&p_empty[t]);
+          }
+          ++pv_cnt;
+          umma_commit(&v_empty[vst]);
+          if (++vst == A3_STAGES) { vst = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warps (16)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int t = (warp - 4) >> 3;                 // query tile
+    const int h = ((warp - 4) >> 2) & 1;           // column half of the kv tile / of O
+    const int ew = warp & 3;                       // TMEM lane quarter
+    const int row = ew * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tS = tmem_base + t * A3_BK + h * 64 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + h * 32 + lane_off;
+    uint8_t* const pb = sP + t * A3_P + h * 16384 + row * 128;
+    float* const xm = xchg + (t * 2 + h) * 128 + row;          // my slot
+    float* const xo = xchg + (t * 2 + (1 - h)) * 128 + row;    // the other half's slot
+    const uint32_t bar_id = 1 + t;
+    const float c = p.scale_log2;
+    uint32_t kv_cnt = 0;
+    uint32_t item_cnt = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
+      const int qp = item % p.q_pairs;
+      const int head = (item / p.q_pairs) % p.H;
+      const int seq = item / (p.q_pairs * p.H);
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++kv_cnt) {
+        mbar_wait(&s_full[t], kv_cnt & 1);
+        tc_fence_after();
+        float s[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(tS, r0);
+          tmem_ld_32x32(tS + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);
+        const int valid = p.Lk - j * A3_BK - h * 64;   // keys of my half that exist
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
+        }
+        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+        for (int i = 4; i < 64; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+          mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+        }
+        const float mloc = fmaxf(mx0, mx1);
+        // lazy rescale: refresh the running max only when some row of this tile outgrew it by 2^TAU
+        const bool need = !((mloc - m) * c <= A3_TAU);     // true for m = -inf (first tile) and NaN-safe
+        if (bar_red_or(bar_id, 256, need)) {
+          *xm = mloc;
+          named_bar_sync(bar_id, 256);
+          const float m_new = fmaxf(m, fmaxf(mloc, *xo));
+          if (j > 0) {
+            const float f = ex2_approx((m - m_new) * c);
+            mbar_wait(&o_full[t], (kv_cnt - 1) & 1);       // P(j-1) V(j-1) has landed
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32(tO, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st_32x32(tO, r);
+            tmem_st_wait();
+            tc_fence_before();
+            l *= f;
+          }
+          m = m_new;
+        }
+        const float mc = m * c;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
+          s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
+          s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
+          s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
+          sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
+        }
+        l += (sum0 + sum1) + (sum2 + sum3);
+        mbar_wait(&p_empty[t], (kv_cnt & 1) ^ 1);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 u;
+          u.x = pack16x2<BF16>(s[ch * 8 + 0], s[ch * 8 + 1]);
+          u.y = pack16x2<BF16>(s[ch * 8 + 2], s[ch * 8 + 3]);
+          u.z = pack16x2<BF16>(s[ch * 8 + 4], s[ch * 8 + 5]);
+          u.w = pack16x2<BF16>(s[ch * 8 + 6], s[ch * 8 + 7]);
+          *reinterpret_cast<uint4*>(pb + ((ch ^ (row & 7)) << 4)) = u;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[t]);
+      }
+      // ---- epilogue of the item: O / l
+      mbar_wait(&o_full[t], (kv_cnt - 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(tO, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_free[t]);
+      *xm = l;
+      named_bar_sync(bar_id, 256);
+      const float inv = 1.0f / (l + *xo);
+      named_bar_sync(bar_id, 256);                         // slots are reused by the next item's first tile
+      const int qrow = (qp * 2 + t) * A3_BQ + row;
+      if (qrow < p.Lq) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(p.o) + (static_cast<int64_t>(seq) * p.Lq + qrow) * p.ldo +
+                        head * A3_D + h * 32;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 u;
+          u.x = pack16x2<BF16>(__uint_as_float(r[ch * 8 + 0]) * inv, __uint_as_float(r[ch * 8 + 1]) * inv);
+          u.y = pack16x2<BF16>(__uint_as_float(r[ch * 8 + 2]) * inv, __uint_as_float(r[ch * 8 + 3]) * inv);
+          u.z = pack16x2<BF16>(__uint_as_float(r[ch * 8 + 4]) * inv, __uint_as_float(r[ch * 8 + 5]) * inv);
+          u.w = pack16x2<BF16>(__uint_as_float(r[ch * 8 + 6]) * inv, __uint_as_float(r[ch * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + ch * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <bool BF16, int EMU>
+int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const Attn3Params& p,
+                      cudaStream_t stream) {
+  auto kern = attention3_kernel<BF16, EMU>;
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  kern<<<grid, A3_THREADS, A3_SMEM, stream>>>(tQ, tK, tV, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace iggt
+
+using namespace iggt;
+
+extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                     int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
+                                     int head_dim, float scale, int dtype, iggt_stream_t stream) {
+  if (head_dim != 64) return -1;
+  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return -1;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -2;
+  if (dtype != 0 && dtype != 1) return -3;
+  const TmDtype dt = dtype ? TM_BF16 : TM_F16;
+  CUtensorMap tQ, tK, tV;
+  if (make_tmap_2d(&tQ, dt, q, (uint64_t)num_seq * Lq, (uint64_t)H * 64, ldq, 64, A3_BQ)) return -4;
+  if (make_tmap_2d(&tK, dt, k, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldk, 64, A3_BK)) return -4;
+  if (make_tmap_2d(&tV, dt, v, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldv, 64, A3_BK)) return -4;
+  Attn3Params p;
+  p.Lq = Lq; p.Lk = Lk; p.H = H; p.num_seq = num_seq;
+  const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ;
+  p.q_pairs = (q_tiles + 1) / 2;
+  p.total_items = num_seq * H * p.q_pairs;
+  p.ldo = ldo; p.o = o;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); return e ? atoi(e) : 0; }();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (emu == 1) return dtype ? launch_attention3<true, 1>(tQ, tK, tV, p, s) : launch_attention3<false, 1>(tQ, tK, tV, p, s);
+  if (emu == 2) return dtype ? launch_attention3<true, 2>(tQ, tK, tV, p, s) : launch_attention3<false, 2>(tQ, tK, tV, p, s);
+  return dtype ? launch_attention3<true, 0>(tQ, tK, tV, p, s) : launch_attention3<false, 0>(tQ, tK, tV, p, s);
+}
