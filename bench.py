@@ -161,10 +161,22 @@ def run_b200(args):
     images_host = images_host.contiguous().pin_memory()
     images_dev = images_host.to(dev)
 
-    def step(imgs):
+    def eager_step(imgs):
         if world > 1:
             return forward_sharded(model, imgs, rank, world)
         return model(imgs)
+
+    step = eager_step
+    graphed = False
+    if not args.no_graph and not args.quick:
+        from iggt_official_b200.graphs import GraphedForward
+        try:
+            g_step = GraphedForward(eager_step)
+            g_step(images_dev)                     # capture now; fall back to eager launches if it fails
+            torch.cuda.synchronize()
+            step, graphed = g_step, True
+        except Exception as e:                     # pragma: no cover
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -198,6 +210,11 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (ops.STATS["launches"] - launches0) // args.steps
+    if graphed:                                    # replays bypass the Python counter: count one eager forward
+        c0 = ops.STATS["launches"]
+        eager_step(images_dev)
+        torch.cuda.synchronize()
+        launches = ops.STATS["launches"] - c0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end through the public API: H2D of the images + D2H of every prediction, each step
@@ -227,7 +244,7 @@ def run_b200(args):
     # ---- per-kernel trace (separate steps, CUDA events on the launching stream around every launch)
     ops.TRACE = []
     for _ in range(2):
-        step(images_dev)
+        eager_step(images_dev)
     torch.cuda.synchronize()
     trace, ops.TRACE = ops.TRACE, None
     agg = {}
@@ -266,7 +283,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches, "cuda_graph": graphed,
             "e2e": {"value": args.views / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "kernel_shares": shares,
@@ -321,6 +338,7 @@ def main():
     ap.add_argument("--part", action="store_true", help="IGGT with the part path (needs an even patch grid, e.g. --size 532)")
     ap.add_argument("--ref-views", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="profiling mode: warm-up + steps only (run this under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -102,7 +102,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* p_empty = p_full + 2;
   uint64_t* o_full = p_empty + 2;          // [2]  committed after every PV
   uint64_t* o_free = o_full + 2;           // [2]  final O of an item has been read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* stagger = o_free + 2;          // [1]  tile A is half-way through the exps of its first kv tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,9 +123,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&o_full[i], 1);   mbar_init(&o_free[i], 256);
     }
     for (int i = 0; i < A3_STAGES; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2);   // released by both tiles' MMA threads
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
     }
+    mbar_init(stagger, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -162,62 +164,58 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (++st == A3_STAGES) { st = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+    } else if ((warp == 1 || warp == 3) && lane == 0) {
+      // ------------------------------------------------------------------ MMA issuers: one thread per query tile.
+      // The two tiles are independent pipelines (they only share the K/V stages), and tile B is started half a
+      // softmax period after tile A (`stagger`), so that the MUFU-heavy exp phase of one tile overlaps the
+      // TMEM-load / max / pack / st.shared phase of the other instead of both bursting on the MUFU unit at once.
+      const int t = warp == 1 ? 0 : 1;
       constexpr uint32_t idesc_qk = make_idesc_f16(A3_BQ, A3_BK, BF16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(A3_BQ, A3_D, BF16, false, true);   // V is MN-major
       int kst = 0; uint32_t kph = 0;
       int vst = 0; uint32_t vph = 0;
-      uint32_t qk_cnt = 0;            // QK issues per tile (same for both tiles)
-      uint32_t pv_cnt = 0;            // PV issues per tile
-      uint32_t item_cnt = 0;
+      uint32_t qk_cnt = 0, pv_cnt = 0, item_cnt = 0;
+      const uint32_t q_addr = smem_u32(sQ + t * A3_TILE);
+      const uint32_t p_addr = smem_u32(sP + t * A3_P);
+      const uint32_t s_tmem = tmem_base + t * A3_BK;
+      const uint32_t o_tmem = tmem_base + 256 + t * 64;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
         const uint32_t qpar = item_cnt & 1;
-        mbar_wait(&q_full[0], qpar);
-        mbar_wait(&q_full[1], qpar);
+        mbar_wait(&q_full[t], qpar);
+        if (t == 1) mbar_wait(stagger, qpar);
         for (int j = -1; j < n_kv; ++j) {
-          // S(j+1) of both tiles: as soon as the softmax warps have pulled S(j) into registers
+          // S(j+1): as soon as the softmax warps have pulled S(j) into registers
           if (j + 1 < n_kv) {
             mbar_wait(&k_full[kst], kph);
+            mbar_wait(&s_empty[t], (qk_cnt & 1) ^ 1);
+            tc_fence_after();
             const uint32_t k_addr = smem_u32(sK + kst * A3_TILE);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              mbar_wait(&s_empty[t], (qk_cnt & 1) ^ 1);
-              tc_fence_after();
-              const uint32_t q_addr = smem_u32(sQ + t * A3_TILE);
-#pragma unroll
-              for (int kk = 0; kk < A3_D / 16; ++kk)
-                umma_f16(tmem_base + t * A3_BK, make_desc_sw128(q_addr + kk * 32, 1024),
-                         make_desc_sw128(k_addr + kk * 32, 1024), idesc_qk, kk != 0 ? 1u : 0u);
-              umma_commit(&s_full[t]);
-            }
-            ++qk_cnt;
+            for (int kk = 0; kk < A3_D / 16; ++kk)
+              umma_f16(s_tmem, make_desc_sw128(q_addr + kk * 32, 1024), make_desc_sw128(k_addr + kk * 32, 1024),
+                       idesc_qk, kk != 0 ? 1u : 0u);
+            umma_commit(&s_full[t]);
             umma_commit(&k_empty[kst]);
+            ++qk_cnt;
             if (++kst == A3_STAGES) { kst = 0; kph ^= 1; }
           } else {
-            umma_commit(&q_empty[0]);
-            umma_commit(&q_empty[1]);
+            umma_commit(&q_empty[t]);
           }
           if (j < 0) continue;
-          // O += P(j) V(j) for both tiles
+          // O += P(j) V(j)
           mbar_wait(&v_full[vst], vph);
+          mbar_wait(&p_full[t], pv_cnt & 1);
+          if (j == 0) mbar_wait(&o_free[t], qpar ^ 1);       // previous item's O has been read out
+          tc_fence_after();
           const uint32_t v_addr = smem_u32(sV + vst * A3_TILE);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&p_full[t], pv_cnt & 1);
-            if (j == 0) mbar_wait(&o_free[t], qpar ^ 1);     // previous item's O has been read out
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP + t * A3_P);
-            const uint32_t d_tmem = tmem_base + 256 + t * 64;
-#pragma unroll
-            for (int kk = 0; kk < A3_BK / 16; ++kk)
-              umma_f16(d_tmem, make_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 1024),
-                       make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
-            umma_commit(&o_full[t]);
-            umma_commit(&p_empty[t]);
-          }
-          ++pv_cnt;
+          for (int kk = 0; kk < A3_BK / 16; ++kk)
+            umma_f16(o_tmem, make_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 1024),
+                     make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
+          umma_commit(&o_full[t]);
+          umma_commit(&p_empty[t]);
           umma_commit(&v_empty[vst]);
+          ++pv_cnt;
           if (++vst == A3_STAGES) { vst = 0; vph ^= 1; }
         }
       }
@@ -295,7 +293,16 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const float mc = m * c;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < 32; i += 4) {
+          s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
+          s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
+          s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
+          s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
+          sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
+        }
+        if (t == 0 && j == 0) mbar_arrive(stagger);          // lets tile B's pipeline start half a period later
+#pragma unroll
+        for (int i = 32; i < 64; i += 4) {
           s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
           s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
           s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
