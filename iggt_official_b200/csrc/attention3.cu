@@ -11,7 +11,8 @@
 // the steady-state loop is: TMEM->reg S, max, exp2, pack, st.shared P.  Row halves agree on the max through a
 // shared-memory exchange that only happens on a rescale; the decision is taken with one bar.red.or per tile.
 //
-// TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+// TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512)
+// (P: 128 keys x 16 bit = 64 columns per query row, only used by the PT variant)
 #include <stdlib.h>
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -52,6 +53,17 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: A (M x K, 16-bit pairs packed per 32-bit column, lane = row) read from TMEM
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // barrier + OR-reduction over `nthreads` threads of named barrier `id`
 __device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
   uint32_t out;
@@ -79,7 +91,8 @@ __device__ __forceinline__ float ex2_emulated(float x) {
   return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
 }
 
-template <bool BF16, int EMU>
+// PT: P goes to TMEM (tcgen05.st, consumed as the A operand of P V straight from tensor memory) instead of shared memory.
+template <bool BF16, int EMU, bool PT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
@@ -179,6 +192,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t p_addr = smem_u32(sP + t * A3_P);
       const uint32_t s_tmem = tmem_base + t * A3_BK;
       const uint32_t o_tmem = tmem_base + 256 + t * 64;
+      const uint32_t p_tmem = tmem_base + 384 + t * 64;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
         const uint32_t qpar = item_cnt & 1;
         mbar_wait(&q_full[t], qpar);
@@ -209,9 +223,14 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc_fence_after();
           const uint32_t v_addr = smem_u32(sV + vst * A3_TILE);
 #pragma unroll
-          for (int kk = 0; kk < A3_BK / 16; ++kk)
-            umma_f16(o_tmem, make_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 1024),
-                     make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < A3_BK / 16; ++kk) {
+            if constexpr (PT)
+              umma_f16_ts(o_tmem, p_tmem + kk * 8, make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv,
+                          (j > 0 || kk != 0) ? 1u : 0u);
+            else
+              umma_f16(o_tmem, make_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 1024),
+                       make_desc_sw128(v_addr + kk * 2048, 1024), idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
+          }
           umma_commit(&o_full[t]);
           umma_commit(&p_empty[t]);
           umma_commit(&v_empty[vst]);
@@ -230,6 +249,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
     const uint32_t tS = tmem_base + t * A3_BK + h * 64 + lane_off;
     const uint32_t tO = tmem_base + 256 + t * 64 + h * 32 + lane_off;
+    const uint32_t tP = tmem_base + 384 + t * 64 + h * 32 + lane_off;
     uint8_t* const pb = sP + t * A3_P + h * 16384 + row * 128;
     float* const xm = xchg + (t * 2 + h) * 128 + row;          // my slot
     float* const xo = xchg + (t * 2 + (1 - h)) * 128 + row;    // the other half's slot
@@ -311,16 +331,26 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         l += (sum0 + sum1) + (sum2 + sum3);
         mbar_wait(&p_empty[t], (kv_cnt & 1) ^ 1);
+        if constexpr (PT) {
+          uint32_t pk[32];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 u;
-          u.x = pack16x2<BF16>(s[ch * 8 + 0], s[ch * 8 + 1]);
-          u.y = pack16x2<BF16>(s[ch * 8 + 2], s[ch * 8 + 3]);
-          u.z = pack16x2<BF16>(s[ch * 8 + 4], s[ch * 8 + 5]);
-          u.w = pack16x2<BF16>(s[ch * 8 + 6], s[ch * 8 + 7]);
-          *reinterpret_cast<uint4*>(pb + ((ch ^ (row & 7)) << 4)) = u;
+          for (int i = 0; i < 32; ++i) pk[i] = pack16x2<BF16>(s[2 * i], s[2 * i + 1]);
+          tc_fence_after();
+          tmem_st_32x32(tP, pk);
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 u;
+            u.x = pack16x2<BF16>(s[ch * 8 + 0], s[ch * 8 + 1]);
+            u.y = pack16x2<BF16>(s[ch * 8 + 2], s[ch * 8 + 3]);
+            u.z = pack16x2<BF16>(s[ch * 8 + 4], s[ch * 8 + 5]);
+            u.w = pack16x2<BF16>(s[ch * 8 + 6], s[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(pb + ((ch ^ (row & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
         mbar_arrive(&p_full[t]);
       }
       // ---- epilogue of the item: O / l
@@ -360,10 +390,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <bool BF16, int EMU>
+template <bool BF16, int EMU, bool PT>
 int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const Attn3Params& p,
                       cudaStream_t stream) {
-  auto kern = attention3_kernel<BF16, EMU>;
+  auto kern = attention3_kernel<BF16, EMU, PT>;
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
@@ -403,8 +433,13 @@ extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, 
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); return e ? atoi(e) : 0; }();
+  static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 0; }();
   cudaStream_t s = (cudaStream_t)stream;
-  if (emu == 1) return dtype ? launch_attention3<true, 1>(tQ, tK, tV, p, s) : launch_attention3<false, 1>(tQ, tK, tV, p, s);
-  if (emu == 2) return dtype ? launch_attention3<true, 2>(tQ, tK, tV, p, s) : launch_attention3<false, 2>(tQ, tK, tV, p, s);
-  return dtype ? launch_attention3<true, 0>(tQ, tK, tV, p, s) : launch_attention3<false, 0>(tQ, tK, tV, p, s);
+  if (pt) {
+    if (emu == 1) return dtype ? launch_attention3<true, 1, true>(tQ, tK, tV, p, s) : launch_attention3<false, 1, true>(tQ, tK, tV, p, s);
+    return dtype ? launch_attention3<true, 0, true>(tQ, tK, tV, p, s) : launch_attention3<false, 0, true>(tQ, tK, tV, p, s);
+  }
+  if (emu == 1) return dtype ? launch_attention3<true, 1, false>(tQ, tK, tV, p, s) : launch_attention3<false, 1, false>(tQ, tK, tV, p, s);
+  if (emu == 2) return dtype ? launch_attention3<true, 2, false>(tQ, tK, tV, p, s) : launch_attention3<false, 2, false>(tQ, tK, tV, p, s);
+  return dtype ? launch_attention3<true, 0, false>(tQ, tK, tV, p, s) : launch_attention3<false, 0, false>(tQ, tK, tV, p, s);
 }
