@@ -433,7 +433,7 @@ extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, 
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); return e ? atoi(e) : 0; }();
-  static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 0; }();
+  static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 1; }();
   cudaStream_t s = (cudaStream_t)stream;
   if (pt) {
     if (emu == 1) return dtype ? launch_attention3<true, 1, true>(tQ, tK, tV, p, s) : launch_attention3<false, 1, true>(tQ, tK, tV, p, s);

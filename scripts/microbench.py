@@ -55,6 +55,13 @@ def main():
         ms_ref = timeit(lambda: torch.matmul(A, w.t(), out=ref_out), flush=flush)
         fl = 2.0 * M * N * K
         res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "cublas_ms": ms_ref, "cublas_tflops": fl / ms_ref / 1e9}
+    # epilogue study on the fc2 shape (K=4096, N=1024): reduce-add vs plain fp32 store vs 16-bit store
+    w2 = (torch.randn(1024, 4096, device=dev) / 64).to(dt)
+    b2 = torch.randn(1024, device=dev)
+    o32 = torch.empty(M, 1024, device=dev)
+    o16 = torch.empty(M, 1024, device=dev, dtype=dt)
+    res["fc2_store32"] = {"ms": timeit(lambda: ops.gemm_store32(a4, w2, b2, out=o32), flush=flush)}
+    res["fc2_store16"] = {"ms": timeit(lambda: ops.gemm_store16(a4, w2, b2, out=o16), flush=flush)}
     # attention: frame (8 seq x 1374) and global (1 seq x 10992)
     qkv = torch.randn(M, 3072, device=dev).to(dt)
     out = torch.empty(M, 1024, device=dev, dtype=dt)
