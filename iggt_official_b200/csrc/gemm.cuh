@@ -51,6 +51,9 @@ struct GemmParams {
   int act_post;
   // EPI_RESID32: round (acc + bias) to 16 bit before the LayerScale multiply (autocast Linear output)
   int round_out16;
+  // stream-K (EPI_RESID32 only): the (tile, k-block) space is cut into gridDim.x equal contiguous ranges; every
+  // CTA reduce-adds the partial product of each tile segment it owns (fp32 atomics in L2 make the pieces add up)
+  int stream_k;
 };
 
 constexpr int GEMM_BM = 128;
@@ -87,6 +90,42 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 3) return x > 0.0f ? x : 0.01f * x;
   return x;
 }
+
+// Work iterator shared by the three warp roles.  Default: whole tiles, static round-robin over the CTAs.
+// stream_k: CTA b owns k-blocks [b*per, (b+1)*per) of the linearised (tile, k-block) space.
+struct WorkIter {
+  int pos, end, step, kb_per_tile, num_tiles;
+  bool sk;
+  __device__ WorkIter(const GemmParams& p) {
+    kb_per_tile = p.num_k_blocks;
+    num_tiles = p.num_m_tiles * p.num_n_tiles;
+    sk = p.stream_k != 0;
+    if (sk) {
+      const long total = static_cast<long>(num_tiles) * kb_per_tile;
+      const long per = (total + gridDim.x - 1) / gridDim.x;
+      const long b = static_cast<long>(blockIdx.x) * per;
+      pos = static_cast<int>(b < total ? b : total);
+      end = static_cast<int>(b + per < total ? b + per : total);
+      step = 0;
+    } else {
+      pos = blockIdx.x; end = num_tiles; step = gridDim.x;
+    }
+  }
+  // next segment: tile index and k-block range [kb0, kb1)
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    if (pos >= end) return false;
+    if (sk) {
+      tile = pos / kb_per_tile;
+      kb0 = pos - tile * kb_per_tile;
+      const int room = end - pos;
+      kb1 = kb0 + room < kb_per_tile ? kb0 + room : kb_per_tile;
+      pos += kb1 - kb0;
+    } else {
+      tile = pos; kb0 = 0; kb1 = kb_per_tile; pos += step;
+    }
+    return true;
+  }
+};
 
 // CONV: A operand comes from a 4-D NHWC tensor map (box {64, TW, TH, 1}); otherwise 2-D [M,K].
 // G = epilogue warpgroups (1 or 2). With G = 2 the column chunks of a tile alternate between two 4-warp
@@ -142,7 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      WorkIter work(p);
+      int tile, kb0, kb1;
+      while (work.next(tile, kb0, kb1)) {
         const int mt = tile / p.num_n_tiles;
         const int nt = tile % p.num_n_tiles;
         int img = 0, y0 = 0, x0 = 0;
@@ -153,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           y0 = (r / p.tiles_x) * CONV_TH;
           x0 = (r % p.tiles_x) * CONV_TW;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
           if constexpr (CONV) {
@@ -179,11 +220,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      WorkIter work(p);
+      int tile, kb0, kb1;
+      while (work.next(tile, kb0, kb1)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * SM::A_BYTES);
@@ -192,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_desc_sw128(a_addr + k * 32, 1024);
             const uint64_t db = make_desc_sw128(b_addr + k * 32, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -224,7 +267,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_count = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    WorkIter work(p);
+    int tile, kb0, kb1;
+    while (work.next(tile, kb0, kb1)) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile % p.num_n_tiles;
       const int n0 = nt * BN;
@@ -247,7 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       named_bar_sync(3, 128 * G);          // every epilogue thread is done with the previous tile's vectors
       for (int i = grp * 128 + gtid; i < BN; i += 128 * G) {
         const int col = n0 + i;
-        vb[i] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        vb[i] = (p.bias && col < p.N && kb0 == 0) ? __ldg(p.bias + col) : 0.f;   // bias rides with the first K segment
         if constexpr (EPI == EPI_RESID32) vg[i] = (p.gamma && col < p.N) ? __ldg(p.gamma + col) : 1.f;
       }
       named_bar_sync(3, 128 * G);
@@ -423,7 +468,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float4 b = *reinterpret_cast<const float4*>(vb + c32 * 32 + i);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             if constexpr (EPI == EPI_RESID32) {
-              if (p.round_out16) {
+              if (p.round_out16 && !p.stream_k) {
                 v[i] = round16<BF16>(v[i]); v[i + 1] = round16<BF16>(v[i + 1]);
                 v[i + 2] = round16<BF16>(v[i + 2]); v[i + 3] = round16<BF16>(v[i + 3]);
               }

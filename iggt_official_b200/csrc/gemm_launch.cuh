@@ -44,6 +44,7 @@ inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, cons
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  if (p.stream_k) grid = device_sm_count();
   if (grid <= 0) return 0;
   kern<<<grid, 128 + 128 * G, smem, stream>>>(tA, tB, tC, p);
   return (int)cudaGetLastError();

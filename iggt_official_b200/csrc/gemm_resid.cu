@@ -1,4 +1,5 @@
 // C-ABI launchers: residual (TMA reduce-add) and fused qkv + q/k-LayerNorm + RoPE epilogues.
+#include <stdlib.h>
 #include "gemm_launch.cuh"
 #include "../../include/iggt_b200.h"
 
@@ -24,10 +25,21 @@ extern "C" int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int6
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma; p.round_out16 = round_out16;
   p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  int bn = choose_bn(p.num_m_tiles, N);
-  if (bn < 128) bn = 128;
-  p.num_n_tiles = (N + bn - 1) / bn;
   p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  // Stream-K: wide (128 x 256) tiles keep the main loop under the 128 B/clk shared-memory ceiling, and cutting the
+  // (tile, k-block) space into equal ranges removes the wave-quantisation loss (N = 1024 gives only 2.3 waves of
+  // such tiles at M = 10992).  IGGT_STREAMK=0 restores whole-tile scheduling (bit-reproducible accumulation order).
+  static const int sk_env = [] { const char* e = getenv("IGGT_STREAMK"); return e ? atoi(e) : 1; }();
+  int bn;
+  {
+    const int tiles256 = p.num_m_tiles * ((N + 255) / 256);
+    const int sms = device_sm_count();
+    const bool quantised = tiles256 % sms != 0 && tiles256 > sms / 2;
+    p.stream_k = (sk_env && N >= 256 && quantised && (long)tiles256 * p.num_k_blocks >= 4L * sms) ? 1 : 0;
+    bn = p.stream_k ? 256 : choose_bn(p.num_m_tiles, N);
+    if (bn < 128) bn = 128;
+  }
+  p.num_n_tiles = (N + bn - 1) / bn;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
