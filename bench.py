@@ -248,7 +248,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     trace, ops.TRACE = ops.TRACE, None
     agg = {}
-    for name, fl, nb, a, b in trace:
+    for name, fl, nb, a, b, _dims in trace:
         d = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += nb; d["n"] += 1
     total_ms = sum(d["ms"] for d in agg.values())

@@ -158,71 +158,51 @@ dpt_tail_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, con
 
 // out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 8 rows per launch
 // (the host loops over row chunks), fp32 activations, 16-bit weights streamed once.  Camera-head Linear layers
-// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.  CTA = 8 warps x 4 output
-// columns; a 2048-wide K-chunk of the activations lives in shared memory; each lane issues the 16-byte weight
-// loads of 4 columns x 4 K-steps (16 in flight) before consuming them, and keeps its 8 x 8 activation slice in
-// registers across the 4 columns.
-constexpr int SK_KC = 2048;   // K chunk staged in smem (8 rows x 2048 fp32 = 64 KB, dynamic)
-constexpr int SK_NC = 4;      // columns per warp
-constexpr int SK_U = 4;       // K-steps (of 256 elements) whose weight loads are issued together
+// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.  One warp owns 8 output columns
+// and keeps 8 x 8 accumulators; per 256-element K step a lane issues 8 independent 16-byte weight loads (two steps
+// in flight) and reads its 8 x 8 activation slice through L1 (every warp of the SM reads the same 64 KB of x, and
+// this kernel uses no shared memory, so the whole 228 KB carve-out is L1).
+constexpr int SK_NC = 8;      // columns per warp
+constexpr int SK_WARPS = 4;   // warps per CTA
 template <bool BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ W, int64_t ldw,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* resid,
                    int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int act) {
-  extern __shared__ __align__(16) float sx[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + warp) * SK_NC;
+  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_NC;
+  if (n0 >= N) return;
   float acc[SK_NC][8];
 #pragma unroll
   for (int c = 0; c < SK_NC; ++c)
 #pragma unroll
     for (int m = 0; m < 8; ++m) acc[c][m] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    const int kc = min(SK_KC, K - k0);
-    __syncthreads();
-    for (int i = threadIdx.x * 4; i < 8 * kc; i += 256 * 4) {
-      const int m = i / kc, kk = i % kc;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M) v = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k0 + kk));
-      *reinterpret_cast<float4*>(sx + m * kc + kk) = v;
+  const uint16_t* wbase = W + static_cast<int64_t>(n0) * ldw;
+#pragma unroll 2
+  for (int k = lane * 8; k < K; k += 256) {
+    uint4 wv[SK_NC];
+#pragma unroll
+    for (int c = 0; c < SK_NC; ++c)
+      wv[c] = (n0 + c < N) ? __ldg(reinterpret_cast<const uint4*>(wbase + c * ldw + k)) : make_uint4(0, 0, 0, 0);
+    float xr[8][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (m < M) {
+        a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k));
+        b = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k + 4));
+      }
+      xr[m][0] = a.x; xr[m][1] = a.y; xr[m][2] = a.z; xr[m][3] = a.w;
+      xr[m][4] = b.x; xr[m][5] = b.y; xr[m][6] = b.z; xr[m][7] = b.w;
     }
-    __syncthreads();
-    for (int kb = 0; kb < kc; kb += 256 * SK_U) {
-      uint4 wv[SK_U][SK_NC];
 #pragma unroll
-      for (int u = 0; u < SK_U; ++u) {
-        const int k = kb + u * 256 + lane * 8;
+    for (int c = 0; c < SK_NC; ++c) {
+      float wf[8];
+      unpack8<BF16>(wv[c], wf);
 #pragma unroll
-        for (int c = 0; c < SK_NC; ++c) {
-          wv[u][c] = make_uint4(0, 0, 0, 0);
-          if (k < kc && n0 + c < N)
-            wv[u][c] = __ldg(reinterpret_cast<const uint4*>(W + static_cast<int64_t>(n0 + c) * ldw + k0 + k));
-        }
-      }
+      for (int m = 0; m < 8; ++m)
 #pragma unroll
-      for (int u = 0; u < SK_U; ++u) {
-        const int k = kb + u * 256 + lane * 8;
-        if (k < kc) {
-          float xr[8][8];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const float4 a = *reinterpret_cast<const float4*>(sx + m * kc + k);
-            const float4 b = *reinterpret_cast<const float4*>(sx + m * kc + k + 4);
-            xr[m][0] = a.x; xr[m][1] = a.y; xr[m][2] = a.z; xr[m][3] = a.w;
-            xr[m][4] = b.x; xr[m][5] = b.y; xr[m][6] = b.z; xr[m][7] = b.w;
-          }
-#pragma unroll
-          for (int c = 0; c < SK_NC; ++c) {
-            float wf[8];
-            unpack8<BF16>(wv[u][c], wf);
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) acc[c][m] = fmaf(xr[m][j], wf[j], acc[c][m]);
-          }
-        }
-      }
+        for (int j = 0; j < 8; ++j) acc[c][m] = fmaf(xr[m][j], wf[j], acc[c][m]);
     }
   }
 #pragma unroll
@@ -232,8 +212,10 @@ skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __r
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
     }
-  if (lane < SK_NC * 8) {
-    const int c = lane / 8, m = lane % 8;
+  // lanes 0..31 write rows m = lane % 8 of columns c = lane / 8 and c + 4
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int c = lane / 8 + half * 4, m = lane % 8;
     const int n = n0 + c;
     if (n < N && m < M) {
       float v = 0.f;
@@ -352,21 +334,19 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
                                 const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo,
                                 int M, int N, int K, int act, int dtype, iggt_stream_t stream) {
   if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
-  if (K > SK_KC && (K % SK_KC)) return -1;
-  const unsigned grid = (N + 8 * SK_NC - 1) / (8 * SK_NC);
+  const unsigned grid = (N + SK_WARPS * SK_NC - 1) / (SK_WARPS * SK_NC);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = 8 * static_cast<size_t>(K < SK_KC ? K : SK_KC) * sizeof(float);
   static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SK_KC * 4);
-    cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SK_KC * 4);
+  if (!configured) {   // no shared memory: let L1 have the whole carve-out (x is re-read by every warp)
+    cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     configured = true;
   }
   for (int m0 = 0; m0 < M; m0 += 8) {   // weights of the later chunks come from L2
     const int mm = M - m0 < 8 ? M - m0 : 8;
     const float* rp = resid ? resid + m0 * ldr : nullptr;
-    if (dtype) skinny_gemm_kernel<true><<<grid, 256, smem, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
-    else skinny_gemm_kernel<false><<<grid, 256, smem, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    if (dtype) skinny_gemm_kernel<true><<<grid, SK_WARPS * 32, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    else skinny_gemm_kernel<false><<<grid, SK_WARPS * 32, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
   }
   return (int)cudaGetLastError();
 }

@@ -51,7 +51,7 @@ def _call(name, flops, nbytes, *args):
         e0.record()
         st = fn(*args)
         e1.record()
-        TRACE.append((name, float(flops), float(nbytes), e0, e1))
+        TRACE.append((name, float(flops), float(nbytes), e0, e1, tuple(a for a in args if isinstance(a, int) and 0 < a < (1 << 24))[:8]))
     _lib.check(st, name)
 
 
