@@ -158,20 +158,20 @@ dpt_tail_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, con
 
 // out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 8 rows per launch
 // (the host loops over row chunks), fp32 activations, 16-bit weights streamed once.  Camera-head Linear layers
-// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound, so no tensor cores.  One warp owns 8 output columns
-// and keeps 8 x 8 accumulators; per 256-element K step a lane issues 8 independent 16-byte weight loads (two steps
-// in flight) and reads its 8 x 8 activation slice through L1 (every warp of the SM reads the same 64 KB of x, and
-// this kernel uses no shared memory, so the whole 228 KB carve-out is L1).
-constexpr int SK_NC = 8;      // columns per warp
-constexpr int SK_WARPS = 4;   // warps per CTA
+// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound (8 rows!), so no tensor cores.
+// CTA = 4 output columns; its 8 warps split K (warp w takes the 256-element K steps w, w+8, ...), keep
+// 4 x 8 accumulators each and are reduced through shared memory.  N/4 CTAs x 8 warps give every SM sub-partition
+// several warps of independent 16-byte weight loads in flight; x (<= 256 KB) is served by L1/L2.
+constexpr int SK_NC = 4;      // columns per CTA
+constexpr int SK_WARPS = 8;   // K-split inside the CTA
 template <bool BF16>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ W, int64_t ldw,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* resid,
                    int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int act) {
+  __shared__ float part[SK_WARPS][SK_NC * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_NC;
-  if (n0 >= N) return;
+  const int n0 = blockIdx.x * SK_NC;
   float acc[SK_NC][8];
 #pragma unroll
   for (int c = 0; c < SK_NC; ++c)
@@ -179,7 +179,7 @@ skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __r
     for (int m = 0; m < 8; ++m) acc[c][m] = 0.f;
   const uint16_t* wbase = W + static_cast<int64_t>(n0) * ldw;
 #pragma unroll 2
-  for (int k = lane * 8; k < K; k += 256) {
+  for (int k = warp * 256 + lane * 8; k < K; k += SK_WARPS * 256) {
     uint4 wv[SK_NC];
 #pragma unroll
     for (int c = 0; c < SK_NC; ++c)
@@ -212,17 +212,22 @@ skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __r
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
     }
-  // lanes 0..31 write rows m = lane % 8 of columns c = lane / 8 and c + 4
+  {  // lane l publishes (c, m) = (l / 8, l % 8)
+    float v = 0.f;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int c = lane / 8 + half * 4, m = lane % 8;
+    for (int cc = 0; cc < SK_NC; ++cc)
+#pragma unroll
+      for (int mm = 0; mm < 8; ++mm) if (cc * 8 + mm == lane) v = acc[cc][mm];
+    part[warp][lane] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int c = lane / 8, m = lane % 8;
     const int n = n0 + c;
     if (n < N && m < M) {
       float v = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < SK_NC; ++cc)
-#pragma unroll
-        for (int mm = 0; mm < 8; ++mm) if (cc == c && mm == m) v = acc[cc][mm];
+      for (int w = 0; w < SK_WARPS; ++w) v += part[w][lane];
       v += bias ? bias[n] : 0.f;
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
@@ -334,7 +339,7 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
                                 const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo,
                                 int M, int N, int K, int act, int dtype, iggt_stream_t stream) {
   if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
-  const unsigned grid = (N + SK_WARPS * SK_NC - 1) / (SK_WARPS * SK_NC);
+  const unsigned grid = (N + SK_NC - 1) / SK_NC;
   cudaStream_t s = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) {   // no shared memory: let L1 have the whole carve-out (x is re-read by every warp)
