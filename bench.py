@@ -108,7 +108,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ref_model, weights  # the one place bench.py executes oracle/: as the CPU baseline
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     S = args.ref_views
     sd = weights.make_state_dict(0, "default", prefixes=("aggregator.", "camera_head.", "depth_head.", "point_head."))
@@ -123,7 +123,8 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     v = S / (ms / 1e3)
-    sample = f"{S} of 8 views at {args.size}x{args.size}, fp32, same heads (global attention over {S} views)"
+    sample = (f"{S} of {args.views} views at {args.size}x{args.size} per step, fp32, same heads "
+              f"(global attention over {S} views), {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "views/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -309,10 +310,17 @@ def trunk_tflop(args):
     return S * (lin + frame + glob + heads)
 
 
+def cpu_threads():
+    """PyTorch's CPU kernels stop scaling (and collapse from oversubscription: 246 s for the 2-view sample with
+    128 threads on the 128-core bench host, 14 s with 8 threads on an 8-core box) well before 128 threads; the CPU
+    legs use at most 32 and report that number as `cores`."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_baseline(args):
-    """Oracle port on the host cores, bounded sample: 1 warm-up-free timed forward of 2 views."""
+    """Oracle port on the host cores, bounded sample: one timed forward of `--ref-views` views."""
     from oracle import ref_model, weights  # checker used as the CPU baseline (never on the product path)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     S = args.ref_views
     sd = weights.make_state_dict(0, "default", prefixes=("aggregator.", "camera_head.", "depth_head.", "point_head."))
@@ -336,7 +344,7 @@ def main():
     ap.add_argument("--size", type=int, default=518)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--part", action="store_true", help="IGGT with the part path (needs an even patch grid, e.g. --size 532)")
-    ap.add_argument("--ref-views", type=int, default=2)
+    ap.add_argument("--ref-views", type=int, default=1, help="views per step of the CPU legs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="profiling mode: warm-up + steps only (run this under ncu)")

@@ -3,6 +3,7 @@
 // im2col, the per-pixel 1x1 + activation tail, a skinny (M <= 32) weight-streaming GEMM and a tiny
 // attention for the S camera tokens.  Coalesced 16-byte accesses, grid-stride loops.
 #include "ptx.cuh"
+#include "tmap.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -158,76 +159,95 @@ dpt_tail_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, con
 
 // out[m, n] = (resid ? resid[m,n] : 0) + gamma[n] * act(x[m,:] . W[n,:] + bias[n]),  M <= 8 rows per launch
 // (the host loops over row chunks), fp32 activations, 16-bit weights streamed once.  Camera-head Linear layers
-// (iggt/heads/camera_head.py:83-154): weight-bandwidth bound (8 rows!), so no tensor cores.
-// CTA = 4 output columns; its 8 warps split K (warp w takes the 256-element K steps w, w+8, ...), keep
-// 4 x 8 accumulators each and are reduced through shared memory.  N/4 CTAs x 8 warps give every SM sub-partition
-// several warps of independent 16-byte weight loads in flight; x (<= 256 KB) is served by L1/L2.
-constexpr int SK_NC = 4;      // columns per CTA
-constexpr int SK_WARPS = 8;   // K-split inside the CTA
+// (iggt/heads/camera_head.py:83-154): 8 rows against up to 33 MB of weights -> purely weight-bandwidth bound, so
+// no tensor cores; the job is to keep ~100 KB of loads in flight per SM.  A producer thread streams
+// {32 columns x 256 k} weight boxes and the matching {8 rows x 256 k} activation box through a 6-stage TMA /
+// mbarrier ring; consumer warp w owns columns 4w..4w+3 (lane = 8 consecutive k), accumulates 4 x 8 dot products
+// in registers and reduces them with shuffles at the end.
+constexpr int SK_COLS = 32;     // columns per CTA
+constexpr int SK_KC = 256;      // k per stage
+constexpr int SK_STAGES = 6;
+constexpr int SK_W_BYTES = SK_COLS * SK_KC * 2;   // 16 KB
+constexpr int SK_X_BYTES = 8 * SK_KC * 4;         // 8 KB
+constexpr int SK_SMEM = SK_STAGES * (SK_W_BYTES + SK_X_BYTES) + 256;
 template <bool BF16>
-__global__ void __launch_bounds__(SK_WARPS * 32)
-skinny_gemm_kernel(const float* __restrict__ x, int64_t ldx, const uint16_t* __restrict__ W, int64_t ldw,
+__global__ void __launch_bounds__(288)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* resid,
                    int64_t ldr, float* out, int64_t ldo, int M, int N, int K, int act) {
-  __shared__ float part[SK_WARPS][SK_NC * 8];
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  uint8_t* sW = sk_smem;
+  uint8_t* sX = sk_smem + SK_STAGES * SK_W_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sX + SK_STAGES * SK_X_BYTES);
+  uint64_t* empty = full + SK_STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * SK_NC;
-  float acc[SK_NC][8];
+  const int n0 = blockIdx.x * SK_COLS;
+  const int nk = (K + SK_KC - 1) / SK_KC;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SK_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], SK_W_BYTES + SK_X_BYTES);
+        tma_load_2d(sW + st * SK_W_BYTES, &tmW, &full[st], kb * SK_KC, n0);
+        tma_load_2d(sX + st * SK_X_BYTES, &tmX, &full[st], kb * SK_KC, 0);
+        if (++st == SK_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  float acc[4][8];
 #pragma unroll
-  for (int c = 0; c < SK_NC; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int m = 0; m < 8; ++m) acc[c][m] = 0.f;
-  const uint16_t* wbase = W + static_cast<int64_t>(n0) * ldw;
-#pragma unroll 2
-  for (int k = warp * 256 + lane * 8; k < K; k += SK_WARPS * 256) {
-    uint4 wv[SK_NC];
-#pragma unroll
-    for (int c = 0; c < SK_NC; ++c)
-      wv[c] = (n0 + c < N) ? __ldg(reinterpret_cast<const uint4*>(wbase + c * ldw + k)) : make_uint4(0, 0, 0, 0);
+  int st = 0; uint32_t ph = 0;
+  for (int kb = 0; kb < nk; ++kb) {
+    mbar_wait(&full[st], ph);
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * SK_W_BYTES) + (warp * 4) * SK_KC + lane * 8;
+    const float* xs = reinterpret_cast<const float*>(sX + st * SK_X_BYTES) + lane * 8;
     float xr[8][8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (m < M) {
-        a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k));
-        b = __ldg(reinterpret_cast<const float4*>(x + m * ldx + k + 4));
-      }
+      const float4 a = *reinterpret_cast<const float4*>(xs + m * SK_KC);
+      const float4 b = *reinterpret_cast<const float4*>(xs + m * SK_KC + 4);
       xr[m][0] = a.x; xr[m][1] = a.y; xr[m][2] = a.z; xr[m][3] = a.w;
       xr[m][4] = b.x; xr[m][5] = b.y; xr[m][6] = b.z; xr[m][7] = b.w;
     }
 #pragma unroll
-    for (int c = 0; c < SK_NC; ++c) {
+    for (int c = 0; c < 4; ++c) {
       float wf[8];
-      unpack8<BF16>(wv[c], wf);
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(w + c * SK_KC), wf);
 #pragma unroll
       for (int m = 0; m < 8; ++m)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[c][m] = fmaf(xr[m][j], wf[j], acc[c][m]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (++st == SK_STAGES) { st = 0; ph ^= 1; }
   }
 #pragma unroll
-  for (int c = 0; c < SK_NC; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
     }
-  {  // lane l publishes (c, m) = (l / 8, l % 8)
+  {
+    const int c = lane / 8, m = lane % 8;
+    const int n = n0 + warp * 4 + c;
     float v = 0.f;
 #pragma unroll
-    for (int cc = 0; cc < SK_NC; ++cc)
+    for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
       for (int mm = 0; mm < 8; ++mm) if (cc * 8 + mm == lane) v = acc[cc][mm];
-    part[warp][lane] = v;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int c = lane / 8, m = lane % 8;
-    const int n = n0 + c;
     if (n < N && m < M) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < SK_WARPS; ++w) v += part[w][lane];
       v += bias ? bias[n] : 0.f;
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
@@ -339,19 +359,31 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
                                 const float* gamma, const float* resid, int64_t ldr, float* out, int64_t ldo,
                                 int M, int N, int K, int act, int dtype, iggt_stream_t stream) {
   if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
-  const unsigned grid = (N + SK_NC - 1) / SK_NC;
+  const unsigned grid = (N + SK_COLS - 1) / SK_COLS;
   cudaStream_t s = (cudaStream_t)stream;
   static bool configured = false;
-  if (!configured) {   // no shared memory: let L1 have the whole carve-out (x is re-read by every warp)
-    cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  if (!configured) {
+    cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
+    cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
     configured = true;
+  }
+  CUtensorMap tW;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {SK_KC, SK_COLS};
+    if (make_tmap(&tW, dtype ? TM_BF16 : TM_F16, 2, W, dims, str, box, false)) return -4;
   }
   for (int m0 = 0; m0 < M; m0 += 8) {   // weights of the later chunks come from L2
     const int mm = M - m0 < 8 ? M - m0 : 8;
     const float* rp = resid ? resid + m0 * ldr : nullptr;
-    if (dtype) skinny_gemm_kernel<true><<<grid, SK_WARPS * 32, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
-    else skinny_gemm_kernel<false><<<grid, SK_WARPS * 32, 0, s>>>(x + m0 * ldx, ldx, (const uint16_t*)W, ldw, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    CUtensorMap tX;
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)mm};
+    uint64_t str[1] = {(uint64_t)ldx * 4};
+    uint32_t box[2] = {SK_KC, 8};
+    if (make_tmap(&tX, TM_F32, 2, x + m0 * ldx, dims, str, box, false)) return -4;
+    if (dtype) skinny_gemm_kernel<true><<<grid, 288, SK_SMEM, s>>>(tW, tX, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    else skinny_gemm_kernel<false><<<grid, 288, SK_SMEM, s>>>(tW, tX, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
   }
   return (int)cudaGetLastError();
 }

@@ -9,7 +9,7 @@ echo "launches per step: $L"
 # torch launches a few kernels of its own per step (copies); capture generously and post-filter by name
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --quick --warmup 1 --steps 1 > gpurun_out/ncu_list_${TAG}.log 2>&1
-for K in attention2_kernel gemm_tcgen05_kernel; do
+for K in attention3_kernel gemm_tcgen05_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:${K} -s 400 -c 3 -f -o gpurun_out/prof_${TAG}_${K} \
       python bench.py --quick --warmup 1 --steps 1 > gpurun_out/ncu_full_${TAG}_${K}.log 2>&1
 done
