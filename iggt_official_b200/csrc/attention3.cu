@@ -38,6 +38,7 @@ struct Attn3Params {
   int64_t ldo;
   void* o;
   float scale_log2;
+  int stagger_at;       // tile A signals tile B's start after this many (x16) exps of its first kv tile (0..4)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -312,22 +313,19 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         const float mc = m * c;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        const bool sig = (t == 0 && j == 0);
+        if (sig && p.stagger_at == 0) mbar_arrive(stagger);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
-          s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
-          s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
-          s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
-          sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
-        }
-        if (t == 0 && j == 0) mbar_arrive(stagger);          // lets tile B's pipeline start half a period later
+        for (int q4 = 0; q4 < 4; ++q4) {
 #pragma unroll
-        for (int i = 32; i < 64; i += 4) {
-          s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
-          s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
-          s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
-          s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
-          sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
+          for (int i = q4 * 16; i < q4 * 16 + 16; i += 4) {
+            s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
+            s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
+            s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
+            s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
+            sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
+          }
+          if (sig && p.stagger_at == q4 + 1) mbar_arrive(stagger);   // lets tile B's pipeline start part-way
         }
         l += (sum0 + sum1) + (sum2 + sum3);
         mbar_wait(&p_empty[t], (kv_cnt & 1) ^ 1);
@@ -432,6 +430,8 @@ extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, 
   p.total_items = num_seq * H * p.q_pairs;
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
+  static const int stag = [] { const char* e = getenv("IGGT_ATTN_STAG"); return e ? atoi(e) : 2; }();
+  p.stagger_at = stag < 0 ? 0 : (stag > 4 ? 4 : stag);
   static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); return e ? atoi(e) : 0; }();
   static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 1; }();
   cudaStream_t s = (cudaStream_t)stream;

@@ -42,13 +42,15 @@ upsample_bilinear_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ 
   const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
   const float sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
   const float sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  const uint32_t per_img = static_cast<uint32_t>(H) * W * cv;     // < 2^31 for every head resolution
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % cv);
-    int64_t pix = i / cv;
-    const int ox = static_cast<int>(pix % W); pix /= W;
-    const int oy = static_cast<int>(pix % H);
-    const int n = static_cast<int>(pix / H);
+    // 32-bit index arithmetic (64-bit div/mod is emulated and dominated this kernel)
+    const int n = static_cast<int>(i / per_img);
+    uint32_t r = static_cast<uint32_t>(i - static_cast<int64_t>(n) * per_img);
+    const int c8 = static_cast<int>(r % static_cast<uint32_t>(cv)); r /= static_cast<uint32_t>(cv);
+    const int ox = static_cast<int>(r % static_cast<uint32_t>(W));
+    const int oy = static_cast<int>(r / static_cast<uint32_t>(W));
     const float fy = sy * oy, fx = sx * ox;
     const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
