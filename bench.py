@@ -193,8 +193,7 @@ def run_b200(args):
         barrier()
         if rank == 0:
             print(json.dumps({"quick": True, "launches_per_step": ops.STATS["launches"] // (args.warmup + args.steps)}))
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- device-resident timing (value)
@@ -277,8 +276,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     value = args.views / (ms * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
@@ -294,8 +292,23 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank teardown.  destroy_process_group() can hang while captured CUDA graphs still reference the
+    NCCL communicator (observed on 2 GPUs: ranks idle until killed), so after a final barrier the ranks flush and
+    leave with os._exit(0) -- everything measured has already been printed."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        os._exit(0)
 
 
 def trunk_tflop(args):
