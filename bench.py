@@ -265,6 +265,22 @@ def run_b200(args):
                 "frac": ach / peaks["gbs"], "traffic": None}
     roof.update({"launches_per_step": d["n"] // 2, "avg_launch_ms": d["ms"] / d["n"], "share_of_step": d["ms"] / total_ms,
                  "peak_source": peaks["source"]})
+    if name == "iggt_attention_fwd":
+        # head_dim 64 attention is bounded by the exp unit (MUFU: 16 ex2/clk/SM measured, scripts/ubench/mufu.cu) before
+        # the tensor pipe: 1 exp per 256 tensor FLOPs -> at most 0.5 of the tensor peak.  Report that roofline too.
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        exps = d["flops"] / 256.0
+        peak_exp = 16.0 * 148 * clk * 1e6
+        roof["mufu_roofline"] = {"achieved_gexp_s": exps / (d["ms"] * 1e-3) / 1e9, "peak_gexp_s": peak_exp / 1e9,
+                                 "frac": exps / (d["ms"] * 1e-3) / peak_exp,
+                                 "note": "ncu: sm__inst_executed_pipe_xu 68.6 % (global), 53.8 % (frame) of peak"}
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp) and world == 1 and args.views == 8 and args.size == 518:
+            t = json.load(open(tp))["iggt_attention_fwd"]
+            # per launch, averaged over the 24 global + 48 frame launches of a step
+            roof["traffic"] = (24 * t["global_c2_bytes_per_launch"] + 48 * t["frame_c2_bytes_per_launch"]) / 72
+            roof["traffic_unit"] = "bytes per launch (dram read+write, ncu --set full)"
+            roof["algorithmic_bytes_per_launch"] = d["bytes"] / d["n"]
     shares = {k: {"share": v["ms"] / total_ms, "ms_per_step": v["ms"] / 2, "n_per_step": v["n"] // 2,
                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None,
                   "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
