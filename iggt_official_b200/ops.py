@@ -304,3 +304,29 @@ def se_scale_add(y0, cx, mean, w1, b1, w2, b2, alpha):
           b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), NB, h * w, C, w1.shape[0], float(alpha),
           _dt(y0), _stream())
     return out
+
+
+def pose_to_cameras(pose_enc, H, W, build_intrinsics=True):
+    """pose_enc [..., 9] fp32 -> (extrinsics [..., 3, 4], intrinsics [..., 3, 3] or None)."""
+    assert pose_enc.is_cuda and pose_enc.dtype == torch.float32 and pose_enc.shape[-1] == 9
+    p = pose_enc.contiguous()
+    n = p.numel() // 9
+    extr = torch.empty(p.shape[:-1] + (3, 4), dtype=torch.float32, device=p.device)
+    intr = torch.empty(p.shape[:-1] + (3, 3), dtype=torch.float32, device=p.device) if build_intrinsics else None
+    _call("iggt_pose_to_cameras", 0, 30.0 * 4 * n, p.data_ptr(), extr.data_ptr(), _ptr(intr), n, H, W, _stream())
+    return extr, intr
+
+
+def unproject_depth(depth, extrinsics, intrinsics, eps=1e-8, z_far=100.0, with_mask=True):
+    """depth [n,H,W] (or [n,H,W,1]) fp32, cameras per view -> (world [n,H,W,3], mask [n,H,W] bool or None)."""
+    if depth.dim() == 4:
+        depth = depth[..., 0]
+    d = depth.contiguous()
+    n, H, W = d.shape
+    e = extrinsics.reshape(n, 3, 4).contiguous()
+    k = intrinsics.reshape(n, 3, 3).contiguous()
+    world = torch.empty((n, H, W, 3), dtype=torch.float32, device=d.device)
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=d.device) if with_mask else None
+    _call("iggt_unproject_depth", 0, 17.0 * d.numel(), d.data_ptr(), e.data_ptr(), k.data_ptr(), world.data_ptr(),
+          _ptr(mask), n, H, W, float(eps), float(z_far), _stream())
+    return world, (mask.bool() if mask is not None else None)

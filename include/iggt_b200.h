@@ -165,6 +165,18 @@ int iggt_se_scale_add(const void* y0, const void* cx, const float* mean, const f
                       const float* w2, const float* b2, void* y, int NB, int64_t hw, int C, int R, float alpha,
                       int dtype, iggt_stream_t stream);
 
+/* ---- Post-processing on the device (what demo.py does on the host after a full D2H copy). */
+
+/* pose_enc [n,9] (T, quaternion xyzw, fov_h, fov_w) -> extrinsics [n,3,4] = [R|T], intrinsics [n,3,3] (may be NULL).
+ * Replaces iggt/utils/pose_enc.py:65-130 + iggt/utils/rotation.py:14-44. */
+int iggt_pose_to_cameras(const float* pose_enc, float* extrinsics, float* intrinsics, int n, int H, int W,
+                         iggt_stream_t stream);
+
+/* depth [n,H,W] + cameras -> world points [n,H,W,3] (X_world = R^T (X_cam - t)) and validity mask [n,H,W] u8
+ * (eps < d < z_far; mask may be NULL).  Replaces iggt/utils/geometry.py:151-300 (per-frame numpy loop). */
+int iggt_unproject_depth(const float* depth, const float* extrinsics, const float* intrinsics, float* world,
+                         uint8_t* mask, int n, int H, int W, float eps, float z_far, iggt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

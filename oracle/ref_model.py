@@ -538,3 +538,44 @@ def forward(sd, images, model="iggt", amp: Optional[torch.dtype] = None, frames_
         pred["part_feat"] = torch.cat(part, 1)
     pred["images"] = images
     return pred
+
+
+# ----------------------------------------------------------------------------- post-processing
+def quat_to_mat(q):
+    """iggt/utils/rotation.py:14-44 (scalar-last quaternion)."""
+    i, j, k, r = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
+def pose_encoding_to_extri_intri(pose_encoding, image_size_hw):
+    """iggt/utils/pose_enc.py:65-130 ("absT_quaR_FoV")."""
+    T, quat = pose_encoding[..., :3], pose_encoding[..., 3:7]
+    fov_h, fov_w = pose_encoding[..., 7], pose_encoding[..., 8]
+    extr = torch.cat([quat_to_mat(quat), T[..., None]], -1)
+    H, W = image_size_hw
+    intr = torch.zeros(pose_encoding.shape[:-1] + (3, 3), dtype=pose_encoding.dtype, device=pose_encoding.device)
+    intr[..., 0, 0] = (W / 2.0) / torch.tan(fov_w / 2.0)
+    intr[..., 1, 1] = (H / 2.0) / torch.tan(fov_h / 2.0)
+    intr[..., 0, 2] = W / 2
+    intr[..., 1, 2] = H / 2
+    intr[..., 2, 2] = 1.0
+    return extr, intr
+
+
+def unproject_depth_map_to_point_map(depth, extr, intr, eps=1e-8, z_far=100.0):
+    """iggt/utils/geometry.py:151-300: X_cam from the pinhole model, X_world = R^T (X_cam - t).
+    depth [S,H,W], extr [S,3,4], intr [S,3,3] -> world [S,H,W,3], mask [S,H,W]."""
+    S, H, W = depth.shape
+    v, u = torch.meshgrid(torch.arange(H, device=depth.device, dtype=depth.dtype),
+                          torch.arange(W, device=depth.device, dtype=depth.dtype), indexing="ij")
+    fu, fv = intr[:, 0, 0, None, None], intr[:, 1, 1, None, None]
+    cu, cv = intr[:, 0, 2, None, None], intr[:, 1, 2, None, None]
+    cam = torch.stack(((u - cu) * depth / fu, (v - cv) * depth / fv, depth), -1)          # [S,H,W,3]
+    R, t = extr[:, :, :3], extr[:, :, 3]
+    world = torch.einsum("sji,shwj->shwi", R, cam - t[:, None, None, :])                    # R^T (x - t)
+    mask = (depth > eps) & (depth < z_far)
+    return world, mask

@@ -8,7 +8,8 @@ import torch
 
 from oracle import ref_model, weights
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt"))
+                if not os.path.basename(p).startswith("postprocess"))
 PREFIXES = ("aggregator.", "camera_head.", "depth_head.", "point_head.", "part_adaptor.", "part_head.")
 
 
