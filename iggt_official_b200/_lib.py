@@ -56,6 +56,9 @@ SIGNATURES = {
     "iggt_pose_to_cameras": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "iggt_unproject_depth": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                              c_void_p],
+    "iggt_resample_h_u8": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "iggt_resample_v_u8_f32": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                               c_int64, c_void_p],
     "iggt_special_tokens": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "launch.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -148,6 +149,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -403,8 +406,7 @@ int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtens
     configured = true;
   }
   const int grid = p.total_items < sms ? p.total_items : sms;
-  kern<<<grid, A3_THREADS, A3_SMEM, stream>>>(tQ, tK, tV, p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(kern, dim3(grid), dim3(A3_THREADS), A3_SMEM, stream, tQ, tK, tV, p);
 }
 
 }  // namespace iggt

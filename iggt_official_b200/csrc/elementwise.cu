@@ -2,6 +2,7 @@
 // patch im2col with ImageNet normalisation, DINOv2 / aggregator token assembly.
 // All are one-pass, vectorised (16 B per lane), warp-shuffle reductions only.
 #include "ptx.cuh"
+#include "launch.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -19,6 +20,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, void* __restrict__ y, int64_t ldy,
                  const float* __restrict__ w, const float* __restrict__ b, float eps, int64_t n_rows_out,
                  int rows_out, int rows_in, int in_off, int out_rows_per_group, int out_off) {
+  griddep_wait();
+  griddep_launch();
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= n_rows_out) return;
   const int lane = threadIdx.x & 31;
@@ -159,8 +162,8 @@ extern "C" int iggt_layernorm(const float* x, int64_t ldx, void* y, int64_t ldy,
   const unsigned grid = static_cast<unsigned>((n + 7) / 8);
   cudaStream_t s = (cudaStream_t)stream;
 #define LN_LAUNCH(VEC, O32, BF)                                                                        \
-  layernorm_kernel<VEC, O32, BF><<<grid, 256, 0, s>>>(x, ldx, y, ldy, w, b, eps, n, rows_out, rows_in, \
-                                                      in_off, out_rows_per_group, out_off)
+  launch_pdl(layernorm_kernel<VEC, O32, BF>, dim3(grid), dim3(256), 0, s, x, ldx, y, ldy, w, b, eps, n, rows_out, rows_in, \
+             in_off, out_rows_per_group, out_off)
   if (C == 1024) {
     if (out_kind == 2) LN_LAUNCH(8, true, false);
     else if (out_kind == 1) LN_LAUNCH(8, false, true);

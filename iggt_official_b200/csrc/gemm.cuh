@@ -14,6 +14,7 @@
 //   1x1 / 3x3 convolutions of the dense heads, iggt/heads/dpt_head.py:234-316
 #pragma once
 #include "ptx.cuh"
+#include "launch.cuh"
 
 namespace iggt {
 
@@ -175,6 +176,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();      // PDL: everything above overlapped the previous kernel's tail
+  griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

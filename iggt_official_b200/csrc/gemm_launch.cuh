@@ -46,8 +46,7 @@ inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, cons
   int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   if (p.stream_k) grid = device_sm_count();
   if (grid <= 0) return 0;
-  kern<<<grid, 128 + 128 * G, smem, stream>>>(tA, tB, tC, p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), smem, stream, tA, tB, tC, p);
 }
 
 }  // namespace iggt

@@ -4,6 +4,7 @@
 // attention for the S camera tokens.  Coalesced 16-byte accesses, grid-stride loops.
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "launch.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -190,6 +191,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     fence_barrier_init();
   }
   __syncthreads();
+  griddep_wait();
+  griddep_launch();
   if (warp == 8) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
@@ -384,8 +387,9 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
     uint64_t str[1] = {(uint64_t)ldx * 4};
     uint32_t box[2] = {SK_KC, 8};
     if (make_tmap(&tX, TM_F32, 2, x + m0 * ldx, dims, str, box, false)) return -4;
-    if (dtype) skinny_gemm_kernel<true><<<grid, 288, SK_SMEM, s>>>(tW, tX, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
-    else skinny_gemm_kernel<false><<<grid, 288, SK_SMEM, s>>>(tW, tX, bias, gamma, rp, ldr, out + m0 * ldo, ldo, mm, N, K, act);
+    float* op = out + m0 * ldo;
+    if (dtype) launch_pdl(skinny_gemm_kernel<true>, dim3(grid), dim3(288), SK_SMEM, s, tW, tX, bias, gamma, rp, ldr, op, ldo, mm, N, K, act);
+    else launch_pdl(skinny_gemm_kernel<false>, dim3(grid), dim3(288), SK_SMEM, s, tW, tX, bias, gamma, rp, ldr, op, ldo, mm, N, K, act);
   }
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,37 @@
+// Programmatic dependent launch (PDL) helpers.  Every hot kernel does its global-memory-free prologue (mbarrier
+// init, TMEM allocation, tensor-map prefetch), then `griddep_wait()` before it touches global memory, and lets the
+// next kernel in the stream begin ITS prologue early with `griddep_launch()`.  With ~730 back-to-back launches per
+// forward (each only 5-100 us once the views are sharded over several GPUs) the launch latency and prologues are
+// otherwise exposed.  IGGT_PDL=0 falls back to plain stream-ordered launches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <utility>
+
+namespace iggt {
+
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline int pdl_enabled() {
+  static const int v = [] { const char* e = getenv("IGGT_PDL"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+}  // namespace iggt

@@ -330,3 +330,27 @@ def unproject_depth(depth, extrinsics, intrinsics, eps=1e-8, z_far=100.0, with_m
     _call("iggt_unproject_depth", 0, 17.0 * d.numel(), d.data_ptr(), e.data_ptr(), k.data_ptr(), world.data_ptr(),
           _ptr(mask), n, H, W, float(eps), float(z_far), _stream())
     return world, (mask.bool() if mask is not None else None)
+
+
+def resample_bicubic_u8(src, kk_h, bounds_h, kk_v, bounds_v, out, oy0=0):
+    """Pillow-exact 8-bit bicubic resize + ToTensor.  src u8 [Hin, Win, 3] (CUDA);  kk_* int32 [size, ksize] and
+    bounds_* int32 [size, 2] are the fixed-point tap tables of each pass (load_fn.precompute_coeffs);  out is a
+    planar fp32 view [3, rows, Wout] (any plane / row stride, unit column stride) that receives output rows
+    [oy0, oy0 + rows) of the resized image divided by 255."""
+    assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous()
+    assert out.is_cuda and out.dtype == torch.float32 and out.dim() == 3 and out.shape[0] == 3 and out.stride(2) == 1
+    for t in (kk_h, bounds_h, kk_v, bounds_v):
+        assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()
+    h_in, w_in, _ = src.shape
+    w_out, rows = kk_h.shape[0], out.shape[1]
+    assert out.shape[2] == w_out and oy0 >= 0 and oy0 + rows <= kk_v.shape[0]
+    bv = bounds_v[oy0:oy0 + rows].cpu()
+    first = int(bv[0, 0])                                  # source rows the vertical pass of this window touches
+    last = int(bv[-1, 0] + bv[-1, 1])
+    assert 0 <= first < last <= h_in
+    tmp = torch.empty((last - first, w_out, 3), dtype=torch.uint8, device=src.device)
+    _call("iggt_resample_h_u8", 0, float((last - first) * 3 * (w_in + w_out)), src[first:].data_ptr(), w_in * 3,
+          last - first, w_out, kk_h.data_ptr(), bounds_h.data_ptr(), kk_h.shape[1], tmp.data_ptr(), _stream())
+    _call("iggt_resample_v_u8_f32", 0, float(tmp.numel() + out.numel() * 4), tmp.data_ptr(), w_out, kk_v.data_ptr(),
+          bounds_v.data_ptr(), kk_v.shape[1], first, oy0, rows, out.data_ptr(), out.stride(0), out.stride(1), _stream())
+    return out

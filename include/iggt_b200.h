@@ -177,6 +177,22 @@ int iggt_pose_to_cameras(const float* pose_enc, float* extrinsics, float* intrin
 int iggt_unproject_depth(const float* depth, const float* extrinsics, const float* intrinsics, float* world,
                          uint8_t* mask, int n, int H, int W, float eps, float z_far, iggt_stream_t stream);
 
+/* ---- Pre-processing on the device (what iggt/utils/load_fn.py:82-98 does on the host with Pillow + torchvision).
+ * Bit-exact restatement of Pillow's 8-bit ImagingResample: kk = fixed-point (22 fractional bits) filter taps
+ * [out_size, ksize] and bounds = (first tap, tap count) pairs [out_size, 2], both built on the host in double. */
+
+/* Horizontal pass: src u8 [rows, *, 3] (row stride in bytes) -> dst u8 [rows, w_out, 3].
+ * Replaces `img.resize(..., BICUBIC)`'s horizontal pass (iggt/utils/load_fn.py:82). */
+int iggt_resample_h_u8(const uint8_t* src, int64_t src_row_stride, int rows, int w_out, const int32_t* kk,
+                       const int32_t* bounds, int ksize, uint8_t* dst, iggt_stream_t stream);
+
+/* Vertical pass + ToTensor: tmp u8 [*, w_out, 3] (row 0 of tmp is source row y_shift) -> planar fp32 x/255 for output
+ * rows [oy0, oy0 + out_rows), written at dst[c * plane_stride + r * row_stride + x].
+ * Replaces the vertical pass of `img.resize` + `to_tensor(img)` + the crop / pad of iggt/utils/load_fn.py:82-98. */
+int iggt_resample_v_u8_f32(const uint8_t* tmp, int w_out, const int32_t* kk, const int32_t* bounds, int ksize,
+                           int y_shift, int oy0, int out_rows, float* dst, int64_t plane_stride, int64_t row_stride,
+                           iggt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
