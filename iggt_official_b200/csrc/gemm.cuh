@@ -63,13 +63,16 @@ constexpr int GEMM_THREADS = 256;
 constexpr int CONV_TW = 16;
 constexpr int CONV_TH = 8;
 
-template <int BN>
+// PAIR: the CTA is one half of a cta_group::2 pair working on a 256 x BN tile; it stages its own 128 rows of A and
+// HALF of the B tile (BN/2 weight rows) per k-block, so the per-SM smem fill drops from 48 KB to 32 KB per k-block
+// at BN = 256 (the 1-CTA kernel is bound by exactly that traffic: 97 B/clk of TMA writes + 96 B/clk of MMA reads).
+template <int BN, bool PAIR = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 16384;                 // 128 rows x 128 B staging tile
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int STAGES = PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
   static constexpr int VEC_BYTES = BN * 4 + (BN * 4 > 1024 ? BN * 4 : 1024);   // bias[BN] + (gamma[BN] | q/k-norm vectors [4][64])
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STG_BYTES + 256 /*barriers*/ + VEC_BYTES;
 };
@@ -97,19 +100,20 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 struct WorkIter {
   int pos, end, step, kb_per_tile, num_tiles;
   bool sk;
-  __device__ WorkIter(const GemmParams& p) {
+  // `worker` of `workers`: the CTA (or CTA pair) index and count
+  __device__ WorkIter(const GemmParams& p, int worker, int workers) {
     kb_per_tile = p.num_k_blocks;
     num_tiles = p.num_m_tiles * p.num_n_tiles;
     sk = p.stream_k != 0;
     if (sk) {
       const long total = static_cast<long>(num_tiles) * kb_per_tile;
-      const long per = (total + gridDim.x - 1) / gridDim.x;
-      const long b = static_cast<long>(blockIdx.x) * per;
+      const long per = (total + workers - 1) / workers;
+      const long b = static_cast<long>(worker) * per;
       pos = static_cast<int>(b < total ? b : total);
       end = static_cast<int>(b + per < total ? b + per : total);
       step = 0;
     } else {
-      pos = blockIdx.x; end = num_tiles; step = gridDim.x;
+      pos = worker; end = num_tiles; step = workers;
     }
   }
   // next segment: tile index and k-block range [kb0, kb1)
@@ -132,11 +136,14 @@ struct WorkIter {
 // G = epilogue warpgroups (1 or 2). With G = 2 the column chunks of a tile alternate between two 4-warp
 // groups (each TMEM lane quarter is then read by two warps), doubling epilogue issue slots and halving
 // the registers available per thread (384 threads) -- used for every epilogue except the qkv one.
-template <int BN, int EPI, bool BF16, bool CONV, int G>
+// PAIR = cta_group::2: launched as clusters of two CTAs; p.num_m_tiles then counts 256-row tile pairs and CTA `rank`
+// of the pair owns the 128-row sub-tile 2 * mt + rank (a sub-tile past the end of the problem is all TMA zero fill
+// on the way in and clipped on the way out).
+template <int BN, int EPI, bool BF16, bool CONV, int G, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using SM = GemmSmem<BN>;
+  using SM = GemmSmem<BN, PAIR>;
   constexpr int STAGES = SM::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -153,7 +160,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = the CTA that issues the pair's MMAs
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -167,13 +176,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4 * G);
+      mbar_init(&tempty_bar[i], 4 * G * (PAIR ? 2 : 1));   // PAIR: the epilogue warps of both CTAs release rank 0's
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<2 * BN>(tmem_slot);
+    else tmem_alloc<2 * BN>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();      // PDL: everything above overlapped the previous kernel's tail
@@ -184,10 +197,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      WorkIter work(p);
+      WorkIter work(p, worker, workers);
       int tile, kb0, kb1;
       while (work.next(tile, kb0, kb1)) {
-        const int mt = tile / p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
         const int nt = tile % p.num_n_tiles;
         int img = 0, y0 = 0, x0 = 0;
         if constexpr (CONV) {
@@ -199,31 +212,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+          int dy = 0, dx = 0, c0 = 0;
           if constexpr (CONV) {
             const int cblocks = p.conv_C / GEMM_BK;
             const int tap = kb / cblocks;
-            const int c0 = (kb % cblocks) * GEMM_BK;
-            int dy = 0, dx = 0;
+            c0 = (kb % cblocks) * GEMM_BK;
             if (p.conv_taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-            tma_load_4d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], c0, x0 + dx, y0 + dy, img);
-          } else {
-            tma_load_2d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM);
           }
-          tma_load_2d(smem_b + stage * SM::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN);
+          if constexpr (PAIR) {
+            // both CTAs' bytes are credited to rank 0's barrier; rank 0 posts the expectation for the pair
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
+            const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+            if constexpr (CONV) tma_load_4d_pair(smem_a + stage * SM::A_BYTES, &tmA, fb, c0, x0 + dx, y0 + dy, img);
+            else tma_load_2d_pair(smem_a + stage * SM::A_BYTES, &tmA, fb, kb * GEMM_BK, mt * GEMM_BM);
+            tma_load_2d_pair(smem_b + stage * SM::B_BYTES, &tmB, fb, kb * GEMM_BK,
+                             nt * BN + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+            if constexpr (CONV) tma_load_4d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], c0, x0 + dx, y0 + dy, img);
+            else tma_load_2d(smem_a + stage * SM::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM);
+            tma_load_2d(smem_b + stage * SM::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, BF16, false, false);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN, BF16, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      WorkIter work(p);
+      WorkIter work(p, worker, workers);
       int tile, kb0, kb1;
       while (work.next(tile, kb0, kb1)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -238,12 +260,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_desc_sw128(a_addr + k * 32, 1024);
             const uint64_t db = make_desc_sw128(b_addr + k * 32, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_pair(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            else umma_f16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (of both CTAs) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -270,10 +297,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t store_count = 0;
-    WorkIter work(p);
+    WorkIter work(p, worker, workers);
     int tile, kb0, kb1;
+    // releasing an accumulator stage: one arrival per epilogue warp on the MMA issuer's (rank 0's) barrier
+    auto release_acc = [&](int a) {
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&tempty_bar[a], 0));
+      else mbar_arrive(&tempty_bar[a]);
+    };
     while (work.next(tile, kb0, kb1)) {
-      const int mt = tile / p.num_n_tiles;
+      const int mt = (tile / p.num_n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
       const int nt = tile % p.num_n_tiles;
       const int n0 = nt * BN;
       int img = 0, y0 = 0, x0 = 0;
@@ -285,7 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         y0 = (r / p.tiles_x) * CONV_TH;
         x0 = (r % p.tiles_x) * CONV_TW;
         const int yy = y0 + row / CONV_TW, xx = x0 + row % CONV_TW;
-        grow = (yy < p.H && xx < p.W) ? ((long)img * p.H + yy) * p.W + xx : -1;
+        grow = (yy < p.H && xx < p.W && img < p.NB) ? ((long)img * p.H + yy) * p.W + xx : -1;
       } else {
         grow = (long)mt * GEMM_BM + row;
         if (grow >= p.M) grow = -1;
@@ -308,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (grp >= nvalid) {               // nothing to read for this group: release immediately
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) release_acc(acc);
         }
 #pragma unroll 1
         for (int c64 = grp; c64 < nvalid; c64 += G) {
@@ -329,7 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // last TMEM read of this tile by this warp: release the accumulator stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc(acc);
           }
           {
 #pragma unroll
@@ -447,7 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (grp >= nvalid) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) release_acc(acc);
         }
 #pragma unroll 1
         for (int c32 = grp; c32 < nvalid; c32 += G) {
@@ -461,7 +493,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (c32 + G >= nvalid) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc(acc);
           }
           float v[32];
 #pragma unroll
@@ -506,10 +538,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer can still touch it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 

@@ -7,8 +7,9 @@ using namespace iggt;
 
 namespace {
 template <int EPI, bool BF16>
-int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+int dispatch_bn(int bn, bool pair, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                 const GemmParams& p, cudaStream_t s) {
+  if (pair) return launch_gemm_kernel<256, EPI, BF16, false, true>(tA, tB, tC, p, s);
   switch (bn) {
     case 256: return launch_gemm_kernel<256, EPI, BF16, false>(tA, tB, tC, p, s);
     default: return launch_gemm_kernel<128, EPI, BF16, false>(tA, tB, tC, p, s);
@@ -31,22 +32,28 @@ extern "C" int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int6
   // such tiles at M = 10992).  IGGT_STREAMK=0 restores whole-tile scheduling (bit-reproducible accumulation order).
   static const int sk_env = [] { const char* e = getenv("IGGT_STREAMK"); return e ? atoi(e) : 1; }();
   int bn;
+  bool pair;
   {
-    const int tiles256 = p.num_m_tiles * ((N + 255) / 256);
-    const int sms = device_sm_count();
-    const bool quantised = tiles256 % sms != 0 && tiles256 > sms / 2;
-    p.stream_k = (sk_env && N >= 256 && quantised && (long)tiles256 * p.num_k_blocks >= 4L * sms) ? 1 : 0;
+    // with CTA pairs the unit of scheduling is a 256 x 256 tile on one of SMs/2 pairs
+    const bool pair256 = use_pair(PAIR_RESID, 256, p.num_m_tiles);
+    const int m256 = pair256 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    const int tiles256 = m256 * ((N + 255) / 256);
+    const int workers = pair256 ? device_sm_count() / 2 : device_sm_count();
+    const bool quantised = tiles256 % workers != 0 && tiles256 > workers / 2;
+    p.stream_k = (sk_env && N >= 256 && quantised && (long)tiles256 * p.num_k_blocks >= 4L * workers) ? 1 : 0;
     bn = p.stream_k ? 256 : choose_bn(p.num_m_tiles, N);
     if (bn < 128) bn = 128;
+    pair = use_pair(PAIR_RESID, bn, p.num_m_tiles);
+    if (pair) p.num_m_tiles = m256;
   }
   p.num_n_tiles = (N + bn - 1) / bn;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
-  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, bn)) return -4;
+  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, pair ? bn / 2 : bn)) return -4;
   if (make_tmap_2d(&tC, TM_F32, x, M, N, ldx, 32, GEMM_BM)) return -4;
-  return dtype ? dispatch_bn<EPI_RESID32, true>(bn, tA, tB, tC, p, (cudaStream_t)stream)
-               : dispatch_bn<EPI_RESID32, false>(bn, tA, tB, tC, p, (cudaStream_t)stream);
+  return dtype ? dispatch_bn<EPI_RESID32, true>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream)
+               : dispatch_bn<EPI_RESID32, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
 }
 
 extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv,
@@ -68,13 +75,15 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   int bn = choose_bn(p.num_m_tiles, N);
   if (bn < 128) bn = 128;
+  const bool pair = use_pair(PAIR_QKV, bn, p.num_m_tiles);
+  if (pair) p.num_m_tiles = (p.num_m_tiles + 1) / 2;
   p.num_n_tiles = (N + bn - 1) / bn;
   p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
-  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, bn)) return -4;
+  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, pair ? bn / 2 : bn)) return -4;
   if (make_tmap_2d(&tC, dt, qkv, M, N, ldo, 64, GEMM_BM)) return -4;
-  return dtype ? dispatch_bn<EPI_QKV, true>(bn, tA, tB, tC, p, (cudaStream_t)stream)
-               : dispatch_bn<EPI_QKV, false>(bn, tA, tB, tC, p, (cudaStream_t)stream);
+  return dtype ? dispatch_bn<EPI_QKV, true>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream)
+               : dispatch_bn<EPI_QKV, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
 }

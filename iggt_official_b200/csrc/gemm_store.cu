@@ -7,8 +7,9 @@ using namespace iggt;
 namespace {
 
 template <int EPI, bool BF16>
-int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+int dispatch_bn(int bn, bool pair, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                 const GemmParams& p, cudaStream_t s) {
+  if (pair) return launch_gemm_kernel<256, EPI, BF16, false, true>(tA, tB, tC, p, s);
   switch (bn) {
     case 256: return launch_gemm_kernel<256, EPI, BF16, false>(tA, tB, tC, p, s);
     case 128: return launch_gemm_kernel<128, EPI, BF16, false>(tA, tB, tC, p, s);
@@ -26,23 +27,25 @@ int gemm_common(int epi, const void* A, int64_t lda, const void* W, int64_t ldw,
   p.M = M; p.N = N; p.K = K;
   p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int bn = choose_bn(p.num_m_tiles, N);
+  const bool pair = use_pair(PAIR_STORE, bn, p.num_m_tiles);
+  if (pair) p.num_m_tiles = (p.num_m_tiles + 1) / 2;
   p.num_n_tiles = (N + bn - 1) / bn;
   p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
-  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, bn)) return -4;
+  if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, pair ? bn / 2 : bn)) return -4;
   if (out32) {
     if (make_tmap_2d(&tC, TM_F32, out, M, N, ldo, 32, GEMM_BM)) return -4;
   } else {
     if (make_tmap_2d(&tC, dt, out, M, N, ldo, 64, GEMM_BM)) return -4;
   }
   if (epi == EPI_STORE16) {
-    return dtype ? dispatch_bn<EPI_STORE16, true>(bn, tA, tB, tC, p, stream)
-                 : dispatch_bn<EPI_STORE16, false>(bn, tA, tB, tC, p, stream);
+    return dtype ? dispatch_bn<EPI_STORE16, true>(bn, pair, tA, tB, tC, p, stream)
+                 : dispatch_bn<EPI_STORE16, false>(bn, pair, tA, tB, tC, p, stream);
   }
-  return dtype ? dispatch_bn<EPI_STORE32, true>(bn, tA, tB, tC, p, stream)
-               : dispatch_bn<EPI_STORE32, false>(bn, tA, tB, tC, p, stream);
+  return dtype ? dispatch_bn<EPI_STORE32, true>(bn, pair, tA, tB, tC, p, stream)
+               : dispatch_bn<EPI_STORE32, false>(bn, pair, tA, tB, tC, p, stream);
 }
 
 }  // namespace

@@ -28,7 +28,8 @@ def ops():
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,N,K,act", [(300, 320, 192, 0), (2748, 4096, 1024, 1), (128, 64, 64, 2), (77, 32, 128, 3),
-                                        (1000, 768, 2048, 0)])
+                                        (1000, 768, 2048, 0),
+                                        (1102, 4096, 256, 1)])   # 9 row tiles: CTA pairs with a half-empty last pair
 def test_gemm_store16(ops, dtype, M, N, K, act):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
@@ -57,7 +58,8 @@ def test_gemm_store16_addend(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (2748, 1024, 4096), (9, 2048, 2048)])
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (2748, 1024, 4096), (9, 2048, 2048),
+                                   (1102, 2048, 512)])            # stream-K over CTA pairs, odd row-tile count
 def test_gemm_resid32(ops, dtype, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
@@ -111,8 +113,9 @@ def _rope_ref(t, pos):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("qk_norm", [False, True])
-def test_gemm_qkv(ops, dtype, qk_norm):
-    C, K, gh, gw, S = 1024, 1024, 5, 7, 3
+@pytest.mark.parametrize("gh,gw,S", [(5, 7, 3), (13, 16, 5)])      # 1 row tile / 9 row tiles (CTA pairs)
+def test_gemm_qkv(ops, dtype, qk_norm, gh, gw, S):
+    C, K = 1024, 1024
     T = 5 + gh * gw
     M = S * T
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -181,7 +184,10 @@ def test_layernorm(ops, out_dtype, C):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,taps,act,use_res", [(2, 37, 37, 256, 256, 9, 2, True), (1, 20, 50, 64, 128, 9, 0, False),
                                                               (2, 19, 19, 1024, 256, 9, 0, False), (1, 30, 30, 128, 32, 9, 2, False),
-                                                              (2, 37, 37, 256, 256, 1, 0, False)])
+                                                              (2, 37, 37, 256, 256, 1, 0, False),
+                                                              # 143 spatial tiles x 256 channels: CTA pairs, odd count
+                                                              (1, 88, 208, 64, 256, 9, 2, True),
+                                                              (1, 88, 208, 64, 256, 1, 0, False)])
 def test_conv_nhwc(ops, dtype, NB, H, W, Cin, Cout, taps, act, use_res):
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).to(dtype)
@@ -423,3 +429,19 @@ def test_channel_attention_pieces(ops, dtype):
     s = torch.sigmoid(F.relu(m @ w1.t() + b1) @ w2.t() + b2)
     ref = y0.float() + 0.01 * cx.float() * s[:, None, None, :]
     assert _relmax(out, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("mask", ["0", "15"])
+def test_gemm_cta_pair_modes(mask):
+    """The GEMM / conv parity tests again with CTA pairs (cta_group::2) forced off (0) and on for every caller (15);
+    the library reads IGGT_PAIR once per process, so this runs them in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("IGGT_PAIR_CHILD"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, IGGT_PAIR=mask, IGGT_PAIR_CHILD="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                          "gemm_store16 or gemm_resid32 or gemm_qkv or conv_nhwc or gemm_store32"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
