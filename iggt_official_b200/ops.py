@@ -354,3 +354,35 @@ def resample_bicubic_u8(src, kk_h, bounds_h, kk_v, bounds_v, out, oy0=0):
     _call("iggt_resample_v_u8_f32", 0, float(tmp.numel() + out.numel() * 4), tmp.data_ptr(), w_out, kk_v.data_ptr(),
           bounds_v.data_ptr(), kk_v.shape[1], first, oy0, rows, out.data_ptr(), out.stride(0), out.stride(1), _stream())
     return out
+
+
+def knn_mean_features(points, feats, k, return_graph=False):
+    """points [n,3] fp32, feats [n,F] fp32 (or None) -> mean over each point's k nearest OTHER points of their feature
+    rows [n,F] (and, with return_graph, (idx [n,k] int32, d2 [n,k])).  Exact; the only library call is the radix sort
+    of the Morton codes (the search is exact for any ordering, the curve only tightens the tile boxes)."""
+    assert points.is_cuda and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 3
+    pts = points.contiguous()
+    n = pts.shape[0]
+    assert 0 < n < 2 ** 31 and 0 < k <= 32
+    dev = pts.device
+    lo, hi = pts.amin(0).contiguous(), pts.amax(0).contiguous()
+    codes = torch.empty(n, dtype=torch.int64, device=dev)
+    _call("iggt_knn_morton", 0, 20.0 * n, pts.data_ptr(), n, lo.data_ptr(), hi.data_ptr(), codes.data_ptr(), _stream())
+    order = torch.argsort(codes)
+    nblocks = (n + 255) // 256
+    sorted4 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    aabb = torch.empty((nblocks, 6), dtype=torch.float32, device=dev)
+    _call("iggt_knn_reorder", 0, 36.0 * n, pts.data_ptr(), order.data_ptr(), n, sorted4.data_ptr(), aabb.data_ptr(),
+          _stream())
+    out = None
+    F = 0
+    if feats is not None:
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 2 and feats.shape[0] == n
+        feats = feats.contiguous()
+        F = feats.shape[1]
+        out = torch.empty_like(feats)
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev) if return_graph else None
+    d2 = torch.empty((n, k), dtype=torch.float32, device=dev) if return_graph else None
+    _call("iggt_knn_mean_features", 0, float(n) * (16 + 4 * F * (k + 1)), sorted4.data_ptr(), aabb.data_ptr(), n, k,
+          _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _stream())
+    return (out, idx, d2) if return_graph else out

@@ -193,6 +193,24 @@ int iggt_resample_v_u8_f32(const uint8_t* tmp, int w_out, const int32_t* kk, con
                            int y_shift, int oy0, int out_rows, float* dst, int64_t plane_stride, int64_t row_stride,
                            iggt_stream_t stream);
 
+/* ---- k-NN feature smoothing on the device (iggt/utils/misc.py:24-78: torch_geometric knn_graph + scatter_mean).
+ * Exact search: Morton-ordered tiles of 256 points + bounding boxes, block-pruned brute force (csrc/knn.cu). */
+
+/* 63-bit Morton code of every point [n,3] on a cubic lattice over the bounding box lo[3]..hi[3] (device pointers). */
+int iggt_knn_morton(const float* points, int64_t n, const float* lo, const float* hi, int64_t* codes,
+                    iggt_stream_t stream);
+
+/* order[n] (a permutation, e.g. argsort of the codes) -> sorted4 [n,4] = (x, y, z, original index as int bits) and
+ * aabb [ceil(n/256), 6] = (min xyz, max xyz) of every tile of 256 consecutive sorted points. */
+int iggt_knn_reorder(const float* points, const int64_t* order, int64_t n, float* sorted4, float* aabb,
+                     iggt_stream_t stream);
+
+/* For every point: its k (<= 32) nearest other points (knn_graph(loop=False)); out[n,F] = mean of their rows of
+ * feats[n,F] (scatter_mean), indexed by ORIGINAL point index.  Optional out_idx [n,k] int32 (-1 = none) and
+ * out_d2 [n,k] squared distances.  feats/out may both be NULL when only the graph is wanted. */
+int iggt_knn_mean_features(const float* sorted4, const float* aabb, int64_t n, int k, const float* feats, int F,
+                           float* out, int32_t* out_idx, float* out_d2, iggt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
