@@ -62,7 +62,7 @@ SIGNATURES = {
     "iggt_knn_morton": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "iggt_knn_reorder": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "iggt_knn_mean_features": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                               c_void_p],
+                               c_void_p, c_void_p],
     "iggt_special_tokens": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 

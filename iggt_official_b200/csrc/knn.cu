@@ -89,23 +89,57 @@ __device__ __forceinline__ float box_box_d2(const float* __restrict__ a, const f
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
-// One CTA = one tile of 256 queries (curve order).  KMAX >= k list slots live in registers: slots [0, k) start at +inf
-// (worst first, replaced first), slots [k, KMAX) at -inf (never the worst, never replaced).
+// One CTA = KNN_QT consecutive queries of the curve order (a quarter of a tile: small CTAs keep the bounding box of
+// the queries tight and confine the wait-for-the-slowest-warp at the tile barriers to two warps; ~9 CTAs per SM hide
+// each other's latencies).  KMAX >= k list slots live in registers: slots [0, k) start at +inf (worst first, replaced
+// first), slots [k, KMAX) at -inf (never the worst, never replaced).
+// Candidates that beat the current k-th distance are not inserted on the spot - a lane that inserts would drag the
+// other 31 through ~100 predicated instructions - but parked in a per-thread shared-memory queue (KNN_Q deep) that the
+// whole warp drains together when any lane's queue could overflow and at the end of every tile.
+constexpr int KNN_QT = 64;     // queries per CTA
+constexpr int KNN_Q = 16;      // queue depth per thread
+constexpr int KNN_G = 8;       // candidates between two "is any queue nearly full" votes
+constexpr int KNN_PT = KNN_TILE / KNN_QT;   // candidate points each thread stages per tile
+
 template <int KMAX>
-__global__ void __launch_bounds__(KNN_TILE)
+__global__ void __launch_bounds__(KNN_QT)
 knn_mean_kernel(const float4* __restrict__ sorted, const float* __restrict__ aabb, int64_t n, int nblocks, int k,
                 const float* __restrict__ feats, int F, float* __restrict__ out, int32_t* __restrict__ out_idx,
-                float* __restrict__ out_d2) {
+                float* __restrict__ out_d2, unsigned long long* __restrict__ stats) {
   __shared__ float4 tile[KNN_TILE];
+  __shared__ float tile_box[6];
+  __shared__ float q_d[KNN_Q][KNN_QT];
+  __shared__ int q_i[KNN_Q][KNN_QT];
   __shared__ int list[KNN_TILE];
-  __shared__ int warp_cnt[KNN_TILE / 32];
-  __shared__ float red[KNN_TILE / 32];
-  __shared__ float my_box[6];
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int64_t pos = static_cast<int64_t>(b) * KNN_TILE + t;
+  __shared__ int warp_cnt[KNN_QT / 32];
+  __shared__ float red[6][KNN_QT / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t pos = static_cast<int64_t>(blockIdx.x) * KNN_QT + t;
+  const int b = static_cast<int>(pos / KNN_TILE);          // the candidate tile this CTA's queries live in
   const bool valid = pos < n;
   const float4 q = valid ? sorted[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t < 6) my_box[t] = aabb[static_cast<int64_t>(b) * 6 + t];
+
+  // bounding box of this CTA's queries
+  float my_box[6];
+  {
+    float v[6] = {valid ? q.x : CUDART_INF_F, valid ? q.y : CUDART_INF_F, valid ? q.z : CUDART_INF_F,
+                  valid ? -q.x : CUDART_INF_F, valid ? -q.y : CUDART_INF_F, valid ? -q.z : CUDART_INF_F};
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[a] = fminf(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+      if (lane == 0) red[a][warp] = v[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      float m = red[a][0];
+#pragma unroll
+      for (int w = 1; w < KNN_QT / 32; ++w) m = fminf(m, red[a][w]);
+      my_box[a] = a < 3 ? m : -m;
+    }
+    __syncthreads();
+  }
 
   float dist[KMAX];
   int idx[KMAX];
@@ -113,30 +147,72 @@ knn_mean_kernel(const float4* __restrict__ sorted, const float* __restrict__ aab
   for (int i = 0; i < KMAX; ++i) { dist[i] = (valid && i < k) ? CUDART_INF_F : -CUDART_INF_F; idx[i] = -1; }
   float worst = valid ? CUDART_INF_F : -CUDART_INF_F;   // an idle thread (past the end) never wants anything
   int slot = 0;
+  int queued = 0;
+  unsigned long long st_loaded = 0, st_computed = 0, st_drains = 0;
 
-  auto process_tile = [&](int c) {
-    __syncthreads();                                     // everyone is done with the previous tile
-    const int64_t cp = static_cast<int64_t>(c) * KNN_TILE + t;
-    tile[t] = cp < n ? sorted[cp] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(-1));
-    __syncthreads();
-    const bool want = point_box_d2(q, aabb + static_cast<int64_t>(c) * 6) <= worst * KNN_SLACK;
-    if (!__any_sync(0xffffffffu, want)) return;          // the whole warp skips a tile nobody can improve from
-    const int self = (c == b) ? t : -1;
-#pragma unroll 4
-    for (int j = 0; j < KNN_TILE; ++j) {
-      const float4 cpt = tile[j];                        // shared-memory broadcast
-      const float dx = cpt.x - q.x, dy = cpt.y - q.y, dz = cpt.z - q.z;
-      const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      if (d < worst && j != self) {                      // loop=False: a point is not its own neighbour
+  // merge this thread's parked candidates into its top-k (warp-converged: every lane calls it together)
+  auto drain = [&]() {
+    const int deepest = __reduce_max_sync(0xffffffffu, queued);
+    for (int e = 0; e < deepest; ++e) {
+      const float d = e < queued ? q_d[e][t] : CUDART_INF_F;
+      if (d < worst) {                                   // re-check: the bound may have moved since it was parked
+        const int id = q_i[e][t];
 #pragma unroll
         for (int i = 0; i < KMAX; ++i)
-          if (i == slot) { dist[i] = d; idx[i] = __float_as_int(cpt.w); }
+          if (i == slot) { dist[i] = d; idx[i] = id; }
         worst = -CUDART_INF_F;
 #pragma unroll
         for (int i = 0; i < KMAX; ++i)
           if (dist[i] > worst) { worst = dist[i]; slot = i; }
       }
     }
+    queued = 0;
+    ++st_drains;
+  };
+
+  auto process_tile = [&](int c) {
+    __syncthreads();                                     // everyone is done with the previous tile
+#pragma unroll
+    for (int r = 0; r < KNN_PT; ++r) {
+      const int64_t cp = static_cast<int64_t>(c) * KNN_TILE + r * KNN_QT + t;
+      tile[r * KNN_QT + t] =
+          cp < n ? sorted[cp] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(-1));
+    }
+    if (t < 6) tile_box[t] = aabb[static_cast<int64_t>(c) * 6 + t];
+    __syncthreads();
+    ++st_loaded;
+    const bool want = point_box_d2(q, tile_box) <= worst * KNN_SLACK;
+    if (!__any_sync(0xffffffffu, want)) return;          // the whole warp skips a tile nobody can improve from
+    ++st_computed;
+    const int self = (c == b) ? static_cast<int>(pos - static_cast<int64_t>(b) * KNN_TILE) : -1;
+#pragma unroll 1
+    for (int j0 = 0; j0 < KNN_TILE; j0 += KNN_G) {
+      float d[KNN_G];
+      int id[KNN_G];
+#pragma unroll
+      for (int j = 0; j < KNN_G; ++j) {                  // straight-line: the KNN_G broadcast loads go out together
+        const float4 cpt = tile[j0 + j];
+        const float dx = cpt.x - q.x, dy = cpt.y - q.y, dz = cpt.z - q.z;
+        d[j] = (j0 + j != self) ? fmaf(dz, dz, fmaf(dy, dy, dx * dx)) : CUDART_INF_F;   // loop=False: not its own neighbour
+        id[j] = __float_as_int(cpt.w);
+      }
+      float dmin = d[0];
+#pragma unroll
+      for (int j = 1; j < KNN_G; ++j) dmin = fminf(dmin, d[j]);
+      if (__any_sync(0xffffffffu, dmin < worst)) {
+#pragma unroll
+        for (int j = 0; j < KNN_G; ++j) {
+          if (d[j] < worst) {
+            q_d[queued][t] = d[j];
+            q_i[queued][t] = id[j];
+            ++queued;
+          }
+        }
+        // the next group can park up to KNN_G more per lane: drain while every queue still has that much room
+        if (__any_sync(0xffffffffu, queued > KNN_Q - KNN_G)) drain();
+      }
+    }
+    if (__any_sync(0xffffffffu, queued > 0)) drain();    // fresh bounds for the next tile's box tests
   };
 
   // ---- phase 1: the curve neighbourhood gives every query a first k-th distance
@@ -144,34 +220,44 @@ knn_mean_kernel(const float4* __restrict__ sorted, const float* __restrict__ aab
     const int c = b + ((o & 1) ? (o + 1) / 2 : -(o / 2));   // b, b+1, b-1, b+2, b-2
     if (c >= 0 && c < nblocks) process_tile(c);
   }
-  // ---- phase 2: every other tile whose box is within the largest k-th distance of this query tile
+  // ---- phase 2: every other tile whose box is within the largest k-th distance of this CTA's queries
   for (int c0 = 0; c0 < nblocks; c0 += KNN_TILE) {
     float r2 = worst;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
     __syncthreads();                                     // list / red / warp_cnt of the previous chunk are consumed
-    if (lane == 0) red[warp] = r2;
+    if (lane == 0) red[0][warp] = r2;
     __syncthreads();
-    r2 = red[0];
+    r2 = red[0][0];
 #pragma unroll
-    for (int w = 1; w < KNN_TILE / 32; ++w) r2 = fmaxf(r2, red[w]);
-    const int c = c0 + t;
-    const bool keep = c < nblocks && (c < b - 2 || c > b + 2) &&
-                      box_box_d2(my_box, aabb + static_cast<int64_t>(c) * 6) <= r2 * KNN_SLACK;
-    const uint32_t m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    int base = 0, total = 0;
+    for (int w = 1; w < KNN_QT / 32; ++w) r2 = fmaxf(r2, red[0][w]);
+    const float r2s = r2 * KNN_SLACK;
+    int total = 0;
+#pragma unroll 1
+    for (int r = 0; r < KNN_PT; ++r) {                   // KNN_QT threads test a chunk of KNN_TILE boxes in KNN_PT rounds
+      const int c = c0 + r * KNN_QT + t;
+      const bool keep = c < nblocks && (c < b - 2 || c > b + 2) &&
+                        box_box_d2(my_box, aabb + static_cast<int64_t>(c) * 6) <= r2s;
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) warp_cnt[warp] = __popc(m);
+      __syncthreads();
+      int base = total;
 #pragma unroll
-    for (int w = 0; w < KNN_TILE / 32; ++w) {
-      if (w < warp) base += warp_cnt[w];
-      total += warp_cnt[w];
+      for (int w = 0; w < KNN_QT / 32; ++w) {
+        if (w < warp) base += warp_cnt[w];
+        total += warp_cnt[w];
+      }
+      if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = c;
+      __syncthreads();
     }
-    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = c;
-    __syncthreads();
     for (int i = 0; i < total; ++i) process_tile(list[i]);
   }
 
+  if (stats && lane == 0) {
+    if (warp == 0) atomicAdd(stats + 0, st_loaded);
+    atomicAdd(stats + 1, st_computed);
+    atomicAdd(stats + 2, st_drains);
+  }
   // ---- tail: mean of the neighbours' feature rows (scatter_mean: sum / max(count, 1)), written at the ORIGINAL index
   if (!valid) return;
   const int64_t qid = __float_as_int(q.w);
@@ -234,16 +320,22 @@ extern "C" int iggt_knn_reorder(const float* points, const int64_t* order, int64
 }
 
 extern "C" int iggt_knn_mean_features(const float* sorted4, const float* aabb, int64_t n, int k, const float* feats,
-                                      int F, float* out, int32_t* out_idx, float* out_d2, iggt_stream_t stream) {
+                                      int F, float* out, int32_t* out_idx, float* out_d2, uint64_t* stats,
+                                      iggt_stream_t stream) {
   if (!sorted4 || !aabb || n <= 0 || n >= (1LL << 31) || k <= 0 || k > 32) return -1;
   if ((feats == nullptr) != (out == nullptr) || (feats && F <= 0)) return -1;
   if (!out && !out_idx) return -1;
   const int nblocks = static_cast<int>((n + KNN_TILE - 1) / KNN_TILE);
+  const unsigned grid = static_cast<unsigned>((n + KNN_QT - 1) / KNN_QT);
   const float4* s4 = reinterpret_cast<const float4*>(sorted4);
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 8) knn_mean_kernel<8><<<nblocks, KNN_TILE, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2);
-  else if (k <= 16) knn_mean_kernel<16><<<nblocks, KNN_TILE, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2);
-  else if (k <= 24) knn_mean_kernel<24><<<nblocks, KNN_TILE, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2);
-  else knn_mean_kernel<32><<<nblocks, KNN_TILE, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2);
+  if (k <= 8) knn_mean_kernel<8><<<grid, KNN_QT, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2,
+                                                       reinterpret_cast<unsigned long long*>(stats));
+  else if (k <= 16) knn_mean_kernel<16><<<grid, KNN_QT, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2,
+                                                       reinterpret_cast<unsigned long long*>(stats));
+  else if (k <= 24) knn_mean_kernel<24><<<grid, KNN_QT, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2,
+                                                       reinterpret_cast<unsigned long long*>(stats));
+  else knn_mean_kernel<32><<<grid, KNN_QT, 0, st>>>(s4, aabb, n, nblocks, k, feats, F, out, out_idx, out_d2,
+                                                       reinterpret_cast<unsigned long long*>(stats));
   return (int)cudaGetLastError();
 }

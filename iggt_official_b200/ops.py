@@ -356,7 +356,7 @@ def resample_bicubic_u8(src, kk_h, bounds_h, kk_v, bounds_v, out, oy0=0):
     return out
 
 
-def knn_mean_features(points, feats, k, return_graph=False):
+def knn_mean_features(points, feats, k, return_graph=False, stats=None):
     """points [n,3] fp32, feats [n,F] fp32 (or None) -> mean over each point's k nearest OTHER points of their feature
     rows [n,F] (and, with return_graph, (idx [n,k] int32, d2 [n,k])).  Exact; the only library call is the radix sort
     of the Morton codes (the search is exact for any ordering, the curve only tightens the tile boxes)."""
@@ -384,5 +384,5 @@ def knn_mean_features(points, feats, k, return_graph=False):
     idx = torch.empty((n, k), dtype=torch.int32, device=dev) if return_graph else None
     d2 = torch.empty((n, k), dtype=torch.float32, device=dev) if return_graph else None
     _call("iggt_knn_mean_features", 0, float(n) * (16 + 4 * F * (k + 1)), sorted4.data_ptr(), aabb.data_ptr(), n, k,
-          _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _stream())
+          _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _ptr(stats), _stream())
     return (out, idx, d2) if return_graph else out

@@ -207,9 +207,10 @@ int iggt_knn_reorder(const float* points, const int64_t* order, int64_t n, float
 
 /* For every point: its k (<= 32) nearest other points (knn_graph(loop=False)); out[n,F] = mean of their rows of
  * feats[n,F] (scatter_mean), indexed by ORIGINAL point index.  Optional out_idx [n,k] int32 (-1 = none) and
- * out_d2 [n,k] squared distances.  feats/out may both be NULL when only the graph is wanted. */
+ * out_d2 [n,k] squared distances.  feats/out may both be NULL when only the graph is wanted.  stats (may be NULL):
+ * 3 device counters that are incremented by (tiles staged, warp-tiles searched, queue drains) for profiling. */
 int iggt_knn_mean_features(const float* sorted4, const float* aabb, int64_t n, int k, const float* feats, int F,
-                           float* out, int32_t* out_idx, float* out_d2, iggt_stream_t stream);
+                           float* out, int32_t* out_idx, float* out_d2, uint64_t* stats, iggt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,9 @@ from test_knn import scene                                                 # noq
 
 def main():
     res = {}
-    for name, (s, h, w) in {"C1_3x336x504": (3, 336, 504), "C2_8x518x518": (8, 518, 518)}.items():
-        pts = torch.from_numpy(scene(s, h, w, 7).reshape(-1, 3)).cuda()
+    for name, (s, h, w, outl) in {"C1_3x336x504": (3, 336, 504, 0.01), "C2_8x518x518": (8, 518, 518, 0.01),
+                                  "C2_no_outliers": (8, 518, 518, 0.0)}.items():
+        pts = torch.from_numpy(scene(s, h, w, 7, outliers=outl).reshape(-1, 3)).cuda()
         feats = torch.nn.functional.normalize(torch.randn(pts.shape[0], 8, device="cuda"), dim=1)
         for _ in range(2):
             ops.knn_mean_features(pts, feats, 20)
@@ -33,13 +34,18 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ops.TRACE = []
-        ops.knn_mean_features(pts, feats, 20)
+        stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+        ops.knn_mean_features(pts, feats, 20, stats=stats)
         torch.cuda.synchronize()
+        ctas, warps = (pts.shape[0] + 63) // 64, (pts.shape[0] + 31) // 32      # 64 queries per CTA
+        st = stats.tolist()
         parts = {t[0]: t[3].elapsed_time(t[4]) for t in ops.TRACE}
         ops.TRACE = None
         n = pts.shape[0]
         entry = {"points": n, "k": 20, "F": 8, "ms_total": sorted(ts)[2], "ms_by_kernel": parts,
-                 "mpoints_per_s": n / sorted(ts)[2] / 1e3}
+                 "mpoints_per_s": n / sorted(ts)[2] / 1e3,
+                 "tiles_staged_per_cta": st[0] / ctas, "tiles_searched_per_warp": st[1] / warps,
+                 "candidates_per_query": 256 * st[1] / warps, "queue_drains_per_warp": st[2] / warps}
         if "--cpu" in sys.argv:
             from scipy.spatial import cKDTree
             p64 = pts.cpu().numpy().astype(np.float64)
