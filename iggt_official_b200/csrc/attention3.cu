@@ -40,7 +40,27 @@ struct Attn3Params {
   void* o;
   float scale_log2;
   int stagger_at;       // tile A signals tile B's start after this many (x16) exps of its first kv tile (0..4)
+  int light_tail;       // the last query pair of every (sequence, head) has no rows for tile B (Lq = 1374: 94 rows)
 };
+
+// item -> (query pair, head, sequence, does tile B have rows).  With a light tail the half-weight items are numbered
+// LAST (longest-processing-time-first over the static round-robin): 8 x 16 x (5 + 1/2) pair-items on 148 CTAs finish
+// in 5.0 item-times instead of 6.0, and tile B's MMAs / softmax are skipped outright for them.
+__device__ __forceinline__ bool attn3_item(const Attn3Params& p, int item, int& qp, int& head, int& seq) {
+  int sh;
+  bool b_active = true;
+  if (p.light_tail) {
+    const int full_pairs = p.q_pairs - 1;
+    const int n_full = full_pairs * p.H * p.num_seq;
+    if (item < n_full) { qp = item % full_pairs; sh = item / full_pairs; }
+    else { qp = full_pairs; sh = item - n_full; b_active = false; }
+  } else {
+    qp = item % p.q_pairs; sh = item / p.q_pairs;
+  }
+  head = sh % p.H;
+  seq = sh / p.H;
+  return b_active;
+}
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -157,18 +177,18 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       int st = 0; uint32_t ph = 0;
-      uint32_t item_cnt = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
-        const int qp = item % p.q_pairs;
-        const int head = (item / p.q_pairs) % p.H;
-        const int seq = item / (p.q_pairs * p.H);
+      uint32_t q_cnt[2] = {0, 0};             // per tile: items in which the tile took part
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int qp, head, seq;
+        const bool b_active = attn3_item(p, item, qp, head, seq);
         const int col = head * A3_D;
-        const uint32_t qpar = item_cnt & 1;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&q_empty[t], qpar ^ 1);
+          if (t == 1 && !b_active) continue;
+          mbar_wait(&q_empty[t], (q_cnt[t] & 1) ^ 1);
           mbar_expect_tx(&q_full[t], A3_TILE);
           tma_load_2d(sQ + t * A3_TILE, &tmQ, &q_full[t], col, seq * p.Lq + (qp * 2 + t) * A3_BQ);
+          ++q_cnt[t];
         }
         for (int j = 0; j < n_kv; ++j) {
           const int row = seq * p.Lk + j * A3_BK;
@@ -197,8 +217,23 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t s_tmem = tmem_base + t * A3_BK;
       const uint32_t o_tmem = tmem_base + 256 + t * 64;
       const uint32_t p_tmem = tmem_base + 384 + t * 64;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
-        const uint32_t qpar = item_cnt & 1;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int qp_, head_, seq_;
+        if (!attn3_item(p, item, qp_, head_, seq_) && t == 1) {
+          // tile B has no rows in this item: only keep the shared K/V ring turning (its stages are released by
+          // BOTH tiles; waiting for `full` first keeps this thread from arriving twice in one phase)
+          for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(&k_full[kst], kph);
+            mbar_arrive(&k_empty[kst]);
+            if (++kst == A3_STAGES) { kst = 0; kph ^= 1; }
+            mbar_wait(&v_full[vst], vph);
+            mbar_arrive(&v_empty[vst]);
+            if (++vst == A3_STAGES) { vst = 0; vph ^= 1; }
+          }
+          continue;
+        }
+        const uint32_t qpar = item_cnt & 1;      // items in which THIS tile took part
+        ++item_cnt;
         mbar_wait(&q_full[t], qpar);
         if (t == 1) mbar_wait(stagger, qpar);
         for (int j = -1; j < n_kv; ++j) {
@@ -260,11 +295,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t bar_id = 1 + t;
     const float c = p.scale_log2;
     uint32_t kv_cnt = 0;
-    uint32_t item_cnt = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++item_cnt) {
-      const int qp = item % p.q_pairs;
-      const int head = (item / p.q_pairs) % p.H;
-      const int seq = item / (p.q_pairs * p.H);
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int qp, head, seq;
+      if (!attn3_item(p, item, qp, head, seq) && t == 1) continue;   // no rows for tile B in this item
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < n_kv; ++j, ++kv_cnt) {
         mbar_wait(&s_full[t], kv_cnt & 1);
@@ -281,8 +314,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_before();
         mbar_arrive(&s_empty[t]);
         const int valid = p.Lk - j * A3_BK - h * 64;   // keys of my half that exist
-        if (valid < 64) {
-#pragma unroll
+        if (valid < 64) {                              // warp-uniform, only the ragged last kv tile
+          __syncwarp();                                // keeps this a real branch: if-converted it costs 54 predicated
+#pragma unroll                                         // instructions on EVERY tile (12 % of the softmax loop)
           for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
         }
         float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
@@ -306,7 +340,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tmem_ld_32x32(tO, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 v = fmul2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(f, f));
+              r[i] = __float_as_uint(v.x); r[i + 1] = __float_as_uint(v.y);
+            }
             tmem_st_32x32(tO, r);
             tmem_st_wait();
             tc_fence_before();
@@ -315,22 +352,29 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           m = m_new;
         }
         const float mc = m * c;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        // scale-and-shift and the row sums run as packed fp32 pairs (FFMA2 / FADD2): same IEEE results, half the
+        // issue slots -- the softmax warps are bound by issue slots and MUFU, not by the FMA pipe
+        float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
         const bool sig = (t == 0 && j == 0);
         if (sig && p.stagger_at == 0) mbar_arrive(stagger);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
 #pragma unroll
           for (int i = q4 * 16; i < q4 * 16 + 16; i += 4) {
-            s[i] = EMU >= 1 ? ex2_emulated(fmaf(s[i], c, -mc)) : ex2_approx(fmaf(s[i], c, -mc));
-            s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
-            s[i + 2] = EMU >= 2 ? ex2_emulated(fmaf(s[i + 2], c, -mc)) : ex2_approx(fmaf(s[i + 2], c, -mc));
-            s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
-            sum0 += s[i]; sum1 += s[i + 1]; sum2 += s[i + 2]; sum3 += s[i + 3];
+            float2 a = ffma2(make_float2(s[i], s[i + 1]), c2, nmc2);
+            float2 b = ffma2(make_float2(s[i + 2], s[i + 3]), c2, nmc2);
+            a.x = EMU >= 1 ? ex2_emulated(a.x) : ex2_approx(a.x);
+            a.y = ex2_approx(a.y);
+            b.x = EMU >= 2 ? ex2_emulated(b.x) : ex2_approx(b.x);
+            b.y = ex2_approx(b.y);
+            s[i] = a.x; s[i + 1] = a.y; s[i + 2] = b.x; s[i + 3] = b.y;
+            sum01 = fadd2(sum01, a);
+            sum23 = fadd2(sum23, b);
           }
           if (sig && p.stagger_at == q4 + 1) mbar_arrive(stagger);   // lets tile B's pipeline start part-way
         }
-        l += (sum0 + sum1) + (sum2 + sum3);
+        l += (sum01.x + sum01.y) + (sum23.x + sum23.y);
         mbar_wait(&p_empty[t], (kv_cnt & 1) ^ 1);
         if constexpr (PT) {
           uint32_t pk[32];
@@ -430,6 +474,8 @@ extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, 
   const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ;
   p.q_pairs = (q_tiles + 1) / 2;
   p.total_items = num_seq * H * p.q_pairs;
+  static const int lpt = [] { const char* e = getenv("IGGT_ATTN_LPT"); return e ? atoi(e) : 1; }();
+  p.light_tail = (lpt && (q_tiles & 1) && p.q_pairs > 1) ? 1 : 0;    // odd tile count: the last pair has no tile B
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int stag = [] { const char* e = getenv("IGGT_ATTN_STAG"); return e ? atoi(e) : 2; }();

@@ -367,7 +367,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
               const float4 b = *reinterpret_cast<const float4*>(vb + c64 * 64 + i);
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              const float2 lo = fadd2(make_float2(v[i], v[i + 1]), make_float2(b.x, b.y));
+              const float2 hi = fadd2(make_float2(v[i + 2], v[i + 3]), make_float2(b.z, b.w));
+              v[i] = lo.x; v[i + 1] = lo.y; v[i + 2] = hi.x; v[i + 3] = hi.y;
             }
           }
           if constexpr (EPI == EPI_QKV) {
@@ -407,7 +409,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.act == 1) {
               // autocast: GELU is evaluated on the 16-bit Linear output (iggt/layers/mlp.py:35-36)
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = gelu_fast(round16<BF16>(v[i]));
+              for (int i = 0; i < 64; i += 2) {
+                const float2 g = gelu_fast2(make_float2(round16<BF16>(v[i]), round16<BF16>(v[i + 1])));
+                v[i] = g.x; v[i + 1] = g.y;
+              }
             } else if (p.act) {
 #pragma unroll
               for (int i = 0; i < 64; ++i) v[i] = apply_act(v[i], p.act);
@@ -501,15 +506,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b = *reinterpret_cast<const float4*>(vb + c32 * 32 + i);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            float2 lo = fadd2(make_float2(v[i], v[i + 1]), make_float2(b.x, b.y));
+            float2 hi = fadd2(make_float2(v[i + 2], v[i + 3]), make_float2(b.z, b.w));
             if constexpr (EPI == EPI_RESID32) {
               if (p.round_out16 && !p.stream_k) {
-                v[i] = round16<BF16>(v[i]); v[i + 1] = round16<BF16>(v[i + 1]);
-                v[i + 2] = round16<BF16>(v[i + 2]); v[i + 3] = round16<BF16>(v[i + 3]);
+                lo.x = round16<BF16>(lo.x); lo.y = round16<BF16>(lo.y);
+                hi.x = round16<BF16>(hi.x); hi.y = round16<BF16>(hi.y);
               }
               const float4 g = *reinterpret_cast<const float4*>(vg + c32 * 32 + i);
-              v[i] *= g.x; v[i + 1] *= g.y; v[i + 2] *= g.z; v[i + 3] *= g.w;
+              lo = fmul2(lo, make_float2(g.x, g.y));
+              hi = fmul2(hi, make_float2(g.z, g.w));
             }
+            v[i] = lo.x; v[i + 1] = lo.y; v[i + 2] = hi.x; v[i + 3] = hi.y;
           }
           if constexpr (EPI == EPI_STORE32) {
             if (p.act) {
