@@ -29,7 +29,8 @@ constexpr int A3_THREADS = 640;
 constexpr int A3_TILE = A3_BK * A3_D * 2;     // 16 KB
 constexpr int A3_P = A3_BQ * A3_BK * 2;       // 32 KB
 constexpr int A3_XCHG = 2 * 2 * 128 * 4;      // max / sum exchange: [tile][half][row] fp32
-constexpr int A3_SMEM = A3_TILE * (2 + 2 * A3_STAGES) + 2 * A3_P + A3_XCHG + 512;
+constexpr int A3_SMEM = A3_TILE * (4 + 2 * A3_STAGES) + 2 * A3_P + A3_XCHG + 512;   // Q is double-buffered per tile
+static_assert(A3_SMEM <= 232448, "shared memory budget");
 constexpr float A3_TAU = 8.0f;                // lazy-rescale threshold in log2 units
 
 struct Attn3Params {
@@ -43,24 +44,64 @@ struct Attn3Params {
   int light_tail;       // the last query pair of every (sequence, head) has no rows for tile B (Lq = 1374: 94 rows)
 };
 
-// item -> (query pair, head, sequence, does tile B have rows).  With a light tail the half-weight items are numbered
-// LAST (longest-processing-time-first over the static round-robin): 8 x 16 x (5 + 1/2) pair-items on 148 CTAs finish
-// in 5.0 item-times instead of 6.0, and tile B's MMAs / softmax are skipped outright for them.
-__device__ __forceinline__ bool attn3_item(const Attn3Params& p, int item, int& qp, int& head, int& seq) {
-  int sh;
-  bool b_active = true;
-  if (p.light_tail) {
-    const int full_pairs = p.q_pairs - 1;
-    const int n_full = full_pairs * p.H * p.num_seq;
-    if (item < n_full) { qp = item % full_pairs; sh = item / full_pairs; }
-    else { qp = full_pairs; sh = item - n_full; b_active = false; }
-  } else {
-    qp = item % p.q_pairs; sh = item / p.q_pairs;
+// Work items = (query-tile pair, head, sequence).  When the last pair of every (sequence, head) has no rows for tile B
+// (Lq = 1374: 10.7 tiles) that pair is a half-weight item: tile B's MMAs and softmax are skipped outright for it, and
+// the static schedule is longest-processing-time-first - every CTA first takes its full items round-robin, then the
+// halves go (twice) to the CTAs that got one full item fewer, then round-robin again.  8 x 16 x (5 + 1/2) items on
+// 148 CTAs finish in 5.0 item-times instead of 6.0.  All roles of a CTA walk the same sequence.
+struct Attn3Items {
+  int n_full, n_half, full_pairs, G, c, r;
+  int k;          // position in this CTA's sequence
+  const Attn3Params& p;
+  __device__ Attn3Items(const Attn3Params& p_) : p(p_) {
+    G = gridDim.x; c = blockIdx.x; k = 0;
+    if (p.light_tail) {
+      full_pairs = p.q_pairs - 1;
+      n_half = p.H * p.num_seq;
+      n_full = full_pairs * n_half;
+    } else {
+      full_pairs = p.q_pairs; n_full = p.total_items; n_half = 0;
+    }
+    r = n_full % G;
   }
-  head = sh % p.H;
-  seq = sh / p.H;
-  return b_active;
-}
+  // next item of this CTA: false when done; b_active = tile B has rows
+  __device__ bool next(int& qp, int& head, int& seq, bool& b_active) {
+    const int my_full = (n_full - c + G - 1) / G;            // full items of this CTA (c, c + G, ...)
+    int sh;
+    if (k < my_full) {
+      const int item = c + k * G;
+      qp = item % full_pairs; sh = item / full_pairs; b_active = true;
+    } else {
+      int m = k - my_full;                                   // m-th half item of this CTA
+      int h;
+      if (r > 0) {
+        const int short_ctas = G - r;                        // CTAs [r, G) have one full item fewer
+        if (c >= r) {
+          if (m < 2) h = (c - r) + m * short_ctas;
+          else h = 2 * short_ctas + c + (m - 2) * G;
+          // a CTA whose first-round half does not exist has no later one either (h grows with m)
+        } else {
+          h = 2 * short_ctas + c + m * G;
+        }
+      } else {
+        h = c + m * G;
+      }
+      if (h >= n_half) return false;
+      qp = full_pairs; sh = h; b_active = false;
+    }
+    ++k;
+    head = sh % p.H;
+    seq = sh / p.H;
+    return true;
+  }
+  // the item that follows the current one (for the Q prefetch), without advancing
+  __device__ bool peek(int& qp, int& head, int& seq, bool& b_active) {
+    const int k0 = k;
+    const bool ok = next(qp, head, seq, b_active);
+    k = k0;
+    return ok;
+  }
+};
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -119,15 +160,15 @@ __global__ void __launch_bounds__(A3_THREADS, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 2 * A3_TILE;
+  uint8_t* sQ = smem;                      // [2 buffers][2 tiles]: the next item's Q lands while this one runs
+  uint8_t* sK = sQ + 4 * A3_TILE;
   uint8_t* sV = sK + A3_STAGES * A3_TILE;
   uint8_t* sP = sV + A3_STAGES * A3_TILE;
   float* xchg = reinterpret_cast<float*>(sP + 2 * A3_P);         // [2 tiles][2 halves][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + A3_XCHG);
-  uint64_t* q_full = bars;                 // [2]
-  uint64_t* q_empty = q_full + 2;          // [2]
-  uint64_t* k_full = q_empty + 2;          // [3]
+  uint64_t* q_full = bars;                 // [2 buffers][2 tiles]
+  uint64_t* q_empty = q_full + 4;          // [2 buffers][2 tiles]
+  uint64_t* k_full = q_empty + 4;          // [3]
   uint64_t* k_empty = k_full + A3_STAGES;
   uint64_t* v_full = k_empty + A3_STAGES;
   uint64_t* v_empty = v_full + A3_STAGES;
@@ -151,8 +192,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmV);
   }
   if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);   mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);   mbar_init(&s_empty[i], 256);
       mbar_init(&p_full[i], 256); mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);   mbar_init(&o_free[i], 256);
@@ -177,19 +218,28 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       int st = 0; uint32_t ph = 0;
-      uint32_t q_cnt[2] = {0, 0};             // per tile: items in which the tile took part
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int qp, head, seq;
-        const bool b_active = attn3_item(p, item, qp, head, seq);
-        const int col = head * A3_D;
+      uint32_t q_cnt[2] = {0, 0};             // per tile: Q loads issued (= items in which the tile takes part)
+      // Q of item n of a tile goes to buffer n & 1; it is requested one item ahead (after the first K/V tile of the
+      // previous item has been requested), so a short item (frame attention: 11 kv tiles) never waits for its Q
+      auto load_q = [&](int qp, int head, int seq, bool b_active) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (t == 1 && !b_active) continue;
-          mbar_wait(&q_empty[t], (q_cnt[t] & 1) ^ 1);
-          mbar_expect_tx(&q_full[t], A3_TILE);
-          tma_load_2d(sQ + t * A3_TILE, &tmQ, &q_full[t], col, seq * p.Lq + (qp * 2 + t) * A3_BQ);
+          const uint32_t buf = q_cnt[t] & 1, par = (q_cnt[t] >> 1) & 1;
+          mbar_wait(&q_empty[buf * 2 + t], par ^ 1);
+          mbar_expect_tx(&q_full[buf * 2 + t], A3_TILE);
+          tma_load_2d(sQ + (buf * 2 + t) * A3_TILE, &tmQ, &q_full[buf * 2 + t], head * A3_D,
+                      seq * p.Lq + (qp * 2 + t) * A3_BQ);
           ++q_cnt[t];
         }
+      };
+      Attn3Items items(p);
+      int qp, head, seq, nqp, nhead, nseq;
+      bool b_active, nb;
+      if (items.peek(qp, head, seq, b_active)) load_q(qp, head, seq, b_active);
+      while (items.next(qp, head, seq, b_active)) {
+        const bool has_next = items.peek(nqp, nhead, nseq, nb);
+        const int col = head * A3_D;
         for (int j = 0; j < n_kv; ++j) {
           const int row = seq * p.Lk + j * A3_BK;
           mbar_wait(&k_empty[st], ph ^ 1);
@@ -199,6 +249,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_expect_tx(&v_full[st], A3_TILE);
           tma_load_2d(sV + st * A3_TILE, &tmV, &v_full[st], col, row);
           if (++st == A3_STAGES) { st = 0; ph ^= 1; }
+          if (j == 0 && has_next) load_q(nqp, nhead, nseq, nb);
         }
       }
     } else if ((warp == 1 || warp == 3) && lane == 0) {
@@ -212,14 +263,15 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int kst = 0; uint32_t kph = 0;
       int vst = 0; uint32_t vph = 0;
       uint32_t qk_cnt = 0, pv_cnt = 0, item_cnt = 0;
-      const uint32_t q_addr = smem_u32(sQ + t * A3_TILE);
       const uint32_t p_addr = smem_u32(sP + t * A3_P);
       const uint32_t s_tmem = tmem_base + t * A3_BK;
       const uint32_t o_tmem = tmem_base + 256 + t * 64;
       const uint32_t p_tmem = tmem_base + 384 + t * 64;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int qp_, head_, seq_;
-        if (!attn3_item(p, item, qp_, head_, seq_) && t == 1) {
+      Attn3Items items(p);
+      int qp_, head_, seq_;
+      bool b_active;
+      while (items.next(qp_, head_, seq_, b_active)) {
+        if (!b_active && t == 1) {
           // tile B has no rows in this item: only keep the shared K/V ring turning (its stages are released by
           // BOTH tiles; waiting for `full` first keeps this thread from arriving twice in one phase)
           for (int j = 0; j < n_kv; ++j) {
@@ -232,9 +284,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           continue;
         }
-        const uint32_t qpar = item_cnt & 1;      // items in which THIS tile took part
+        const uint32_t qbuf = item_cnt & 1, qbpar = (item_cnt >> 1) & 1;   // item_cnt: items in which THIS tile took part
+        const uint32_t qpar = item_cnt & 1;
         ++item_cnt;
-        mbar_wait(&q_full[t], qpar);
+        const uint32_t q_addr = smem_u32(sQ + (qbuf * 2 + t) * A3_TILE);
+        mbar_wait(&q_full[qbuf * 2 + t], qbpar);
         if (t == 1) mbar_wait(stagger, qpar);
         for (int j = -1; j < n_kv; ++j) {
           // S(j+1): as soon as the softmax warps have pulled S(j) into registers
@@ -252,7 +306,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             ++qk_cnt;
             if (++kst == A3_STAGES) { kst = 0; kph ^= 1; }
           } else {
-            umma_commit(&q_empty[t]);
+            umma_commit(&q_empty[qbuf * 2 + t]);
           }
           if (j < 0) continue;
           // O += P(j) V(j)
@@ -295,9 +349,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t bar_id = 1 + t;
     const float c = p.scale_log2;
     uint32_t kv_cnt = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int qp, head, seq;
-      if (!attn3_item(p, item, qp, head, seq) && t == 1) continue;   // no rows for tile B in this item
+    Attn3Items items(p);
+    int qp, head, seq;
+    bool b_active;
+    while (items.next(qp, head, seq, b_active)) {
+      if (!b_active && t == 1) continue;                             // no rows for tile B in this item
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < n_kv; ++j, ++kv_cnt) {
         mbar_wait(&s_full[t], kv_cnt & 1);
