@@ -10,7 +10,7 @@ echo "launches per step: $L"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --quick --warmup 1 --steps 1 > gpurun_out/ncu_list_${TAG}.log 2>&1
 for K in attention3_kernel gemm_tcgen05_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:${K} -s 400 -c 3 -f -o gpurun_out/prof_${TAG}_${K} \
+  ncu --set full --clock-control none --import-source on -k regex:${K} -s 300 -c 4 -f -o gpurun_out/prof_${TAG}_${K} \
       python bench.py --quick --warmup 1 --steps 1 > gpurun_out/ncu_full_${TAG}_${K}.log 2>&1
 done
 ls -la gpurun_out/
