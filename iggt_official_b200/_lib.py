@@ -63,6 +63,8 @@ SIGNATURES = {
     "iggt_knn_reorder": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "iggt_knn_mean_features": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p],
+    "iggt_gemm_plan": [c_int, c_int, c_int, c_int, c_void_p],
+    "iggt_attention_schedule": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int],
     "iggt_special_tokens": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 

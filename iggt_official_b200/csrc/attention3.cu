@@ -53,8 +53,9 @@ struct Attn3Items {
   int n_full, n_half, full_pairs, G, c, r;
   int k;          // position in this CTA's sequence
   const Attn3Params& p;
-  __device__ Attn3Items(const Attn3Params& p_) : p(p_) {
-    G = gridDim.x; c = blockIdx.x; k = 0;
+  // G CTAs in the grid, this is CTA c (host-callable so that the schedule itself is unit-tested without a GPU)
+  __host__ __device__ Attn3Items(const Attn3Params& p_, int G_, int c_) : p(p_) {
+    G = G_; c = c_; k = 0;
     if (p.light_tail) {
       full_pairs = p.q_pairs - 1;
       n_half = p.H * p.num_seq;
@@ -65,7 +66,7 @@ struct Attn3Items {
     r = n_full % G;
   }
   // next item of this CTA: false when done; b_active = tile B has rows
-  __device__ bool next(int& qp, int& head, int& seq, bool& b_active) {
+  __host__ __device__ bool next(int& qp, int& head, int& seq, bool& b_active) {
     const int my_full = (n_full - c + G - 1) / G;            // full items of this CTA (c, c + G, ...)
     int sh;
     if (k < my_full) {
@@ -95,7 +96,7 @@ struct Attn3Items {
     return true;
   }
   // the item that follows the current one (for the Q prefetch), without advancing
-  __device__ bool peek(int& qp, int& head, int& seq, bool& b_active) {
+  __host__ __device__ bool peek(int& qp, int& head, int& seq, bool& b_active) {
     const int k0 = k;
     const bool ok = next(qp, head, seq, b_active);
     k = k0;
@@ -233,7 +234,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ++q_cnt[t];
         }
       };
-      Attn3Items items(p);
+      Attn3Items items(p, static_cast<int>(gridDim.x), static_cast<int>(blockIdx.x));
       int qp, head, seq, nqp, nhead, nseq;
       bool b_active, nb;
       if (items.peek(qp, head, seq, b_active)) load_q(qp, head, seq, b_active);
@@ -267,7 +268,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t s_tmem = tmem_base + t * A3_BK;
       const uint32_t o_tmem = tmem_base + 256 + t * 64;
       const uint32_t p_tmem = tmem_base + 384 + t * 64;
-      Attn3Items items(p);
+      Attn3Items items(p, static_cast<int>(gridDim.x), static_cast<int>(blockIdx.x));
       int qp_, head_, seq_;
       bool b_active;
       while (items.next(qp_, head_, seq_, b_active)) {
@@ -349,7 +350,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t bar_id = 1 + t;
     const float c = p.scale_log2;
     uint32_t kv_cnt = 0;
-    Attn3Items items(p);
+    Attn3Items items(p, static_cast<int>(gridDim.x), static_cast<int>(blockIdx.x));
     int qp, head, seq;
     bool b_active;
     while (items.next(qp, head, seq, b_active)) {
@@ -513,6 +514,37 @@ int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtens
 
 using namespace iggt;
 
+namespace {
+void attn3_shape(Attn3Params& p, int num_seq, int Lq, int Lk, int H) {
+  p.Lq = Lq; p.Lk = Lk; p.H = H; p.num_seq = num_seq;
+  const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ;
+  p.q_pairs = (q_tiles + 1) / 2;
+  p.total_items = num_seq * H * p.q_pairs;
+  static const int lpt = [] { const char* e = getenv("IGGT_ATTN_LPT"); return e ? atoi(e) : 1; }();
+  p.light_tail = (lpt && (q_tiles & 1) && p.q_pairs > 1) ? 1 : 0;    // odd tile count: the last pair has no tile B
+}
+}  // namespace
+
+// Host-side view of the kernel's static work schedule (no GPU needed): the items CTA `cta` of a `grid`-CTA launch
+// processes, in order, as (query pair, head, sequence, tile-B-active) quadruples.  Returns the item count (which may
+// exceed max_items; only the first max_items are written) or a negative argument error.
+extern "C" int iggt_attention_schedule(int num_seq, int Lq, int Lk, int H, int grid, int cta, int* items,
+                                       int max_items) {
+  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || grid <= 0 || cta < 0 || cta >= grid) return -1;
+  Attn3Params p{};
+  attn3_shape(p, num_seq, Lq, Lk, H);
+  Attn3Items it(p, grid, cta);
+  int n = 0, qp, head, seq;
+  bool b_active;
+  while (it.next(qp, head, seq, b_active)) {
+    if (items && n < max_items) {
+      items[4 * n] = qp; items[4 * n + 1] = head; items[4 * n + 2] = seq; items[4 * n + 3] = b_active ? 1 : 0;
+    }
+    ++n;
+  }
+  return n;
+}
+
 extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                      int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
                                      int head_dim, float scale, int dtype, iggt_stream_t stream) {
@@ -526,12 +558,7 @@ extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, 
   if (make_tmap_2d(&tK, dt, k, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldk, 64, A3_BK)) return -4;
   if (make_tmap_2d(&tV, dt, v, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldv, 64, A3_BK)) return -4;
   Attn3Params p;
-  p.Lq = Lq; p.Lk = Lk; p.H = H; p.num_seq = num_seq;
-  const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ;
-  p.q_pairs = (q_tiles + 1) / 2;
-  p.total_items = num_seq * H * p.q_pairs;
-  static const int lpt = [] { const char* e = getenv("IGGT_ATTN_LPT"); return e ? atoi(e) : 1; }();
-  p.light_tail = (lpt && (q_tiles & 1) && p.q_pairs > 1) ? 1 : 0;    // odd tile count: the last pair has no tile B
+  attn3_shape(p, num_seq, Lq, Lk, H);
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int stag = [] { const char* e = getenv("IGGT_ATTN_STAG"); return e ? atoi(e) : 2; }();

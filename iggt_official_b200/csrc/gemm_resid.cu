@@ -25,28 +25,11 @@ extern "C" int iggt_gemm_resid32(const void* A, int64_t lda, const void* W, int6
   if (dtype != 0 && dtype != 1) return -3;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma; p.round_out16 = round_out16;
-  p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  // Stream-K: wide (128 x 256) tiles keep the main loop under the 128 B/clk shared-memory ceiling, and cutting the
-  // (tile, k-block) space into equal ranges removes the wave-quantisation loss (N = 1024 gives only 2.3 waves of
-  // such tiles at M = 10992).  IGGT_STREAMK=0 restores whole-tile scheduling (bit-reproducible accumulation order).
-  static const int sk_env = [] { const char* e = getenv("IGGT_STREAMK"); return e ? atoi(e) : 1; }();
-  int bn;
-  bool pair;
-  {
-    // with CTA pairs the unit of scheduling is a 256 x 256 tile on one of SMs/2 pairs
-    const bool pair256 = use_pair(PAIR_RESID, 256, p.num_m_tiles);
-    const int m256 = pair256 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
-    const int tiles256 = m256 * ((N + 255) / 256);
-    const int workers = pair256 ? device_sm_count() / 2 : device_sm_count();
-    const bool quantised = tiles256 % workers != 0 && tiles256 > workers / 2;
-    p.stream_k = (sk_env && N >= 256 && quantised && (long)tiles256 * p.num_k_blocks >= 4L * workers) ? 1 : 0;
-    bn = p.stream_k ? 256 : choose_bn(p.num_m_tiles, N);
-    if (bn < 128) bn = 128;
-    pair = use_pair(PAIR_RESID, bn, p.num_m_tiles);
-    if (pair) p.num_m_tiles = m256;
-  }
-  p.num_n_tiles = (N + bn - 1) / bn;
+  const GemmPlan plan = plan_gemm(EPI_RESID32, M, N, K);
+  const int bn = plan.bn;
+  const bool pair = plan.pair != 0;
+  p.stream_k = plan.stream_k;
+  p.num_m_tiles = plan.m_tiles; p.num_n_tiles = plan.n_tiles; p.num_k_blocks = plan.k_blocks;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
@@ -72,13 +55,10 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   p.qk_norm = qk_norm; p.C = C;
   p.qn_w = qn_w; p.qn_b = qn_b; p.kn_w = kn_w; p.kn_b = kn_b;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.pos_yx = pos_yx; p.T = T > 0 ? T : 1;
-  p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  int bn = choose_bn(p.num_m_tiles, N);
-  if (bn < 128) bn = 128;
-  const bool pair = use_pair(PAIR_QKV, bn, p.num_m_tiles);
-  if (pair) p.num_m_tiles = (p.num_m_tiles + 1) / 2;
-  p.num_n_tiles = (N + bn - 1) / bn;
-  p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const GemmPlan plan = plan_gemm(EPI_QKV, M, N, K);
+  const int bn = plan.bn;
+  const bool pair = plan.pair != 0;
+  p.num_m_tiles = plan.m_tiles; p.num_n_tiles = plan.n_tiles; p.num_k_blocks = plan.k_blocks;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;

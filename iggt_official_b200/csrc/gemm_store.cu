@@ -25,12 +25,10 @@ int gemm_common(int epi, const void* A, int64_t lda, const void* W, int64_t ldw,
   const bool out32 = (epi == EPI_STORE32);
   if (out32 ? (ldo % 4) : (ldo % 8)) return -2;
   p.M = M; p.N = N; p.K = K;
-  p.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  const int bn = choose_bn(p.num_m_tiles, N);
-  const bool pair = use_pair(PAIR_STORE, bn, p.num_m_tiles);
-  if (pair) p.num_m_tiles = (p.num_m_tiles + 1) / 2;
-  p.num_n_tiles = (N + bn - 1) / bn;
-  p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const GemmPlan plan = plan_gemm(epi, M, N, K);
+  const int bn = plan.bn;
+  const bool pair = plan.pair != 0;
+  p.num_m_tiles = plan.m_tiles; p.num_n_tiles = plan.n_tiles; p.num_k_blocks = plan.k_blocks;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   CUtensorMap tA, tB, tC;
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
@@ -49,6 +47,17 @@ int gemm_common(int epi, const void* A, int64_t lda, const void* W, int64_t ldw,
 }
 
 }  // namespace
+
+// Host-only: the schedule the launchers would use for an (epilogue, M, N, K) problem on this device (148 SMs assumed
+// when no GPU is visible).  epi: 0 store16, 1 resid32, 2 qkv (N = 3C), 3 store32.
+// out = {bn, pair, stream_k, m_tiles, n_tiles, k_blocks, grid}.
+extern "C" int iggt_gemm_plan(int epi, int M, int N, int K, int* out) {
+  if (epi < 0 || epi > 3 || M <= 0 || N <= 0 || K <= 0 || !out) return -1;
+  const GemmPlan g = plan_gemm(epi, M, N, K);
+  out[0] = g.bn; out[1] = g.pair; out[2] = g.stream_k; out[3] = g.m_tiles; out[4] = g.n_tiles; out[5] = g.k_blocks;
+  out[6] = g.grid;
+  return 0;
+}
 
 extern "C" int iggt_gemm_store16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
                                  int64_t ldo, int M, int N, int K, int dtype, const float* bias,

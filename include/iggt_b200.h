@@ -177,6 +177,17 @@ int iggt_pose_to_cameras(const float* pose_enc, float* extrinsics, float* intrin
 int iggt_unproject_depth(const float* depth, const float* extrinsics, const float* intrinsics, float* world,
                          uint8_t* mask, int n, int H, int W, float eps, float z_far, iggt_stream_t stream);
 
+/* ---- Host-side schedules (no GPU work, callable without a GPU): what the launchers above decide before launching.
+ * They exist so that tile selection, CTA pairing, stream-K and the attention work distribution are unit-tested. */
+
+/* Schedule of a GEMM launch. epi: 0 store16, 1 resid32, 2 qkv (N = 3C), 3 store32.
+ * out[7] = {bn, pair (cta_group::2), stream_k, m_tiles (256-row pairs when pair), n_tiles, k_blocks, grid}. */
+int iggt_gemm_plan(int epi, int M, int N, int K, int* out);
+
+/* Work items of CTA `cta` of a `grid`-CTA iggt_attention_fwd launch, in processing order, as quadruples
+ * (query-tile pair, head, sequence, tile B has rows); returns their number (first max_items are written). */
+int iggt_attention_schedule(int num_seq, int Lq, int Lk, int H, int grid, int cta, int* items, int max_items);
+
 /* ---- Pre-processing on the device (what iggt/utils/load_fn.py:82-98 does on the host with Pillow + torchvision).
  * Bit-exact restatement of Pillow's 8-bit ImagingResample: kk = fixed-point (22 fractional bits) filter taps
  * [out_size, ksize] and bounds = (first tap, tap count) pairs [out_size, 2], both built on the host in double. */
