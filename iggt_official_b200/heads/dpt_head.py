@@ -91,6 +91,8 @@ class DPTHead(Node):
             pk[f"r{i}.out.b"] = _f32(rn.out_conv.bias, device)
         pk["oc1.w"] = pack_conv3x3(s.output_conv1.weight, dtype, device)
         pk["oc1.b"] = _f32(s.output_conv1.bias, device)
+        if "output_conv2" not in s._modules:          # tracker feature extractor (for_tracker=True): features only
+            return
         oc2 = s.output_conv2
         pk["oc2a.w"] = pack_conv3x3(oc2._modules["0"].weight, dtype, device)
         pk["oc2a.b"] = _f32(oc2._modules["0"].bias, device)

@@ -41,7 +41,8 @@ class _Base(nn.Module, PyTorchModelHubMixin):
         self.camera_head = CameraHead()
         self.point_head = DPTHead(output_dim=4, activation="inv_log", use_point_feat=self._with_part)
         self.depth_head = DPTHead(output_dim=2, activation="exp", use_point_feat=False)
-        self.track_head = Node()
+        from ..heads.track_head import TrackHead
+        self.track_head = TrackHead()
         if self._with_part:
             from ..heads.part_head import PartAdaptor, PartHead
             self.part_adaptor = PartAdaptor()
@@ -70,9 +71,8 @@ class _Base(nn.Module, PyTorchModelHubMixin):
     def forward(self, images: torch.Tensor, query_points: torch.Tensor = None):
         if len(images.shape) == 4:
             images = images.unsqueeze(0)
-        if query_points is not None:
-            raise NotImplementedError("track_head (query_points) is outside the B200 hot path; "
-                                      "use the reference TrackHead on the returned tokens")
+        if query_points is not None and len(query_points.shape) == 2:
+            query_points = query_points.unsqueeze(0)           # vggt.py:179-180
         dt = self._dtype()
         tokens, psi = self.aggregator(images, compute_dtype=dt)
         predictions = {}
@@ -90,6 +90,12 @@ class _Base(nn.Module, PyTorchModelHubMixin):
             maps = self.part_adaptor(tokens, images=images, patch_start_idx=psi, compute_dtype=dt)
             predictions["part_feat"] = self.part_head(maps, point_feature=point_feat, images=images,
                                                       patch_start_idx=psi, compute_dtype=dt)
+        if query_points is not None:                             # vggt.py:220-226
+            track_list, vis, conf = self.track_head(tokens, images=images, patch_start_idx=psi,
+                                                    query_points=query_points, compute_dtype=dt)
+            predictions["track"] = track_list[-1]
+            predictions["vis"] = vis
+            predictions["conf"] = conf
         predictions["images"] = images
         return predictions
 

@@ -386,3 +386,74 @@ def knn_mean_features(points, feats, k, return_graph=False, stats=None):
     _call("iggt_knn_mean_features", 0, float(n) * (16 + 4 * F * (k + 1)), sorted4.data_ptr(), aabb.data_ptr(), n, k,
           _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _ptr(stats), _stream())
     return (out, idx, d2) if return_graph else out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Track head (csrc/track.cu)
+def avgpool2_nhwc(x):
+    """[NB,H,W,C] 16-bit -> [NB,H//2,W//2,C]."""
+    assert x.is_cuda and x.is_contiguous() and x.dim() == 4
+    NB, H, W, C = x.shape
+    y = torch.empty((NB, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    _call("iggt_avgpool2_nhwc", 0, 2.0 * (x.numel() + y.numel()), x.data_ptr(), y.data_ptr(), NB, H, W, C, _dt(x), _stream())
+    return y
+
+
+def sample_bilinear_nhwc(x, coords):
+    """x [NB,H,W,C] 16-bit, coords [NB,R,2] fp32 (x,y) pixels -> [NB,R,C] fp32 (border padding, align_corners)."""
+    assert x.is_cuda and x.is_contiguous() and coords.dtype == torch.float32
+    NB, H, W, C = x.shape
+    coords = coords.contiguous()
+    R = coords.shape[1]
+    out = torch.empty((NB, R, C), dtype=torch.float32, device=x.device)
+    _call("iggt_sample_bilinear_nhwc", 0, 12.0 * out.numel(), x.data_ptr(), coords.data_ptr(), out.data_ptr(), NB, R, H, W,
+          C, _dt(x), _stream())
+    return out
+
+
+def corr_sample(levels, targets, coords, B, N, S, ldo=576):
+    """levels: 7 NHWC [B*S,H_l,W_l,128] 16-bit maps; targets [B*N*S,128], coords [B*N*S,2] fp32 in (b,n,s) row order
+    -> [B*N*S, ldo] 16-bit (7 x 81 correlations, zero padded: the A operand of the corr MLP)."""
+    import ctypes
+    assert len(levels) == 7 and all(l.is_cuda and l.is_contiguous() and l.shape[-1] == 128 for l in levels)
+    assert targets.dtype == torch.float32 and targets.is_contiguous() and coords.dtype == torch.float32
+    coords = coords.contiguous()
+    rows = B * N * S
+    out = torch.empty((rows, ldo), dtype=levels[0].dtype, device=targets.device)
+    ptrs = (ctypes.c_void_p * 7)(*[l.data_ptr() for l in levels])
+    Hs = (ctypes.c_int * 7)(*[l.shape[1] for l in levels])
+    Ws = (ctypes.c_int * 7)(*[l.shape[2] for l in levels])
+    _call("iggt_corr_sample", 2.0 * rows * 7 * 100 * 128, rows * 7.0 * 100 * 256,
+          ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(Hs, ctypes.c_void_p), ctypes.cast(Ws, ctypes.c_void_p),
+          targets.data_ptr(), coords.data_ptr(), out.data_ptr(), B, N, S, ldo, _dt(levels[0]), _stream())
+    return out
+
+
+def track_input(coords, fcorr, tfeat, pos, ref_tok, ln_w, ln_b, S, dtype, ldo=392, want_raw=False):
+    """Rows (b,n,s): coords [rows,2], fcorr / tfeat [rows,128], pos [B*N,388], ref_tok [2,388] (all fp32) ->
+    LayerNorm(388)'d transformer input [rows, ldo] 16-bit (and the fp32 pre-norm rows when want_raw)."""
+    rows = coords.shape[0]
+    for t in (coords, fcorr, tfeat, pos, ref_tok, ln_w, ln_b):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty((rows, ldo), dtype=dtype, device=coords.device)
+    raw = torch.empty((rows, 388), dtype=torch.float32, device=coords.device) if want_raw else None
+    _call("iggt_track_input", 0, rows * (388.0 * 6 + 2 * ldo), coords.data_ptr(), fcorr.data_ptr(), tfeat.data_ptr(),
+          pos.data_ptr(), ref_tok.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), out.data_ptr(), _ptr(raw), rows, S, ldo,
+          1e-5, F16 if dtype == torch.float16 else BF16, _stream())
+    return (out, raw) if want_raw else out
+
+
+def layernorm_rows(x, w, b, eps=1e-5, out32=None, out16=None):
+    """LayerNorm of fp32 rows x [rows,C] (last-dim stride 1, any row pitch) into out32 [rows,C] and / or out16 [rows,>=C]."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, C = x.shape
+    assert out32 is not None or out16 is not None
+    if out32 is not None:
+        assert out32.dtype == torch.float32 and out32.is_contiguous() and tuple(out32.shape) == (rows, C)
+    ld16, dt = 0, 0
+    if out16 is not None:
+        assert out16.is_contiguous() and out16.shape[0] == rows and out16.shape[1] >= C
+        ld16, dt = out16.shape[1], _dt(out16)
+    _call("iggt_layernorm_rows", 0, rows * C * 10.0, x.data_ptr(), x.stride(0), C, w.data_ptr(), b.data_ptr(), float(eps),
+          rows, _ptr(out32), _ptr(out16), ld16, dt, _stream())
+    return out32, out16

@@ -177,6 +177,34 @@ int iggt_pose_to_cameras(const float* pose_enc, float* extrinsics, float* intrin
 int iggt_unproject_depth(const float* depth, const float* extrinsics, const float* intrinsics, float* world,
                          uint8_t* mask, int n, int H, int W, float eps, float z_far, iggt_stream_t stream);
 
+/* ---- Track head (iggt/heads/track_head.py, track_modules/*): the non-GEMM, non-attention pieces. */
+
+/* One pyramid level: x [NB,H,W,C] 16-bit -> y [NB,H/2,W/2,C] (2x2 mean).  Replaces F.avg_pool2d at blocks.py:173. */
+int iggt_avgpool2_nhwc(const void* x, void* y, int NB, int H, int W, int C, int dtype, iggt_stream_t stream);
+
+/* out[n,r,:] fp32 = bilinear sample of x[n] (NHWC 16-bit) at coords[n,r] = (x,y) pixels, align_corners, border
+ * padding.  Replaces sample_features4d (track_modules/utils.py:199-226). */
+int iggt_sample_bilinear_nhwc(const void* x, const float* coords, float* out, int NB, int R, int H, int W, int C,
+                              int dtype, iggt_stream_t stream);
+
+/* Correlation lookup: for every row (b,n,s) and each of the 7 pyramid levels (NHWC [B*S,H_l,W_l,128] 16-bit), the
+ * 9x9 window of <target, fmap>/sqrt(128) around coords / 2^level, bilinear, zero padding -> out 16-bit [rows, ldo]
+ * (7*81 values then zeros).  Replaces CorrBlock.corr_sample (track_modules/blocks.py:187-246). */
+int iggt_corr_sample(const void* const* levels, const int* Hs, const int* Ws, const float* targets, const float* coords,
+                     void* out, int B, int N, int S, int ldo, int dtype, iggt_stream_t stream);
+
+/* Transformer input of one refinement iteration, rows (b,n,s): flow embedding | flows/518 | corr feature | track
+ * feature, + pos[(b,n)] + ref_tok[s>0], LayerNorm(388) -> out 16-bit [rows, ldo]; raw (optional) = fp32 [rows,388]
+ * before the LayerNorm.  Replaces base_track_predictor.py:139-165 + blocks.py:103. */
+int iggt_track_input(const float* coords, const float* fcorr, const float* tfeat, const float* pos,
+                     const float* ref_tok, const float* ln_w, const float* ln_b, void* out, float* raw, int rows, int S,
+                     int ldo, float eps, int dtype, iggt_stream_t stream);
+
+/* LayerNorm over C <= 2048 of fp32 rows (pitch ldx) -> y32 [rows,C] and / or y16 [rows,ld16] zero padded (either may
+ * be NULL).  Used for the 384-wide blocks of the update transformer (track_modules/modules.py:136-218). */
+int iggt_layernorm_rows(const float* x, int64_t ldx, int C, const float* w, const float* b, float eps, int64_t rows,
+                        float* y32, void* y16, int ld16, int dtype, iggt_stream_t stream);
+
 /* ---- Host-side schedules (no GPU work, callable without a GPU): what the launchers above decide before launching.
  * They exist so that tile selection, CTA pairing, stream-K and the attention work distribution are unit-tested. */
 
