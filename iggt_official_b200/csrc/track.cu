@@ -115,7 +115,13 @@ corr_sample_kernel(const CorrParams p) {
   const int s = row % p.S, b = row / (p.S * p.N);
   const int H = p.H[lvl], W = p.W[lvl];
   const float inv = 1.0f / static_cast<float>(1 << lvl);
-  const float cx = p.coords[static_cast<int64_t>(row) * 2] * inv, cy = p.coords[static_cast<int64_t>(row) * 2 + 1] * inv;
+  // A level that has shrunk to ONE pixel along an axis is degenerate in the reference: its sampler normalises with
+  // 2 / max(size - 1, 1) and grid_sample(align_corners=True) maps every coordinate of a size-1 axis to pixel 0
+  // (utils.py:176-196), so all window positions read that pixel.  Reproduced by pinning the centre to 0 and freezing
+  // the window index along that axis (only small inputs get here: 518 x 518 images end at a 4 x 4 level).
+  const bool flat_x = p.W[lvl] == 1, flat_y = p.H[lvl] == 1;
+  const float cx = flat_x ? 0.f : p.coords[static_cast<int64_t>(row) * 2] * inv;
+  const float cy = flat_y ? 0.f : p.coords[static_cast<int64_t>(row) * 2 + 1] * inv;
   const float fx0 = floorf(cx), fy0 = floorf(cy);
   const int x0 = static_cast<int>(fx0) - CORR_R, y0 = static_cast<int>(fy0) - CORR_R;
   const float fx = cx - fx0, fy = cy - fy0;
@@ -139,7 +145,7 @@ corr_sample_kernel(const CorrParams p) {
   if (!live) return;
   uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + static_cast<int64_t>(row) * p.ldo + lvl * CORR_WIN * CORR_WIN;
   for (int k = lane; k < CORR_WIN * CORR_WIN; k += 32) {
-    const int i = k / CORR_WIN, j = k % CORR_WIN;                // i: x offset, j: y offset
+    const int i = flat_x ? CORR_R : k / CORR_WIN, j = flat_y ? CORR_R : k % CORR_WIN;   // i: x offset, j: y offset
     const float* q = &patch[warp][j * CORR_PATCH + i];
     const float v = (q[0] * (1.f - fx) + q[1] * fx) * (1.f - fy) + (q[CORR_PATCH] * (1.f - fx) + q[CORR_PATCH + 1] * fx) * fy;
     o[k] = st16<BF16>(v);
