@@ -11,9 +11,11 @@ Differences from the reference that a caller can observe:
   * CUDA only (no CPU fallback); the 16-bit compute dtype follows the enclosing autocast (fp16 when there is
     none -- the reference would run fp32).
   * S > 12 views works (the reference's frame-chunk path raises TypeError).
-  * `track_head` parameters are kept for checkpoint round-trip; passing `query_points` raises
-    NotImplementedError (out of scope).
+  * `query_points` (track head) is implemented (heads/track_head.py) but stays opt-in
+    (IGGT_TRACK_HEAD=1) until its last kernel fix has been re-verified on a GPU; without the opt-in it raises
+    NotImplementedError as before.
 """
+import os
 from typing import Optional
 
 import torch
@@ -71,8 +73,15 @@ class _Base(nn.Module, PyTorchModelHubMixin):
     def forward(self, images: torch.Tensor, query_points: torch.Tensor = None):
         if len(images.shape) == 4:
             images = images.unsqueeze(0)
-        if query_points is not None and len(query_points.shape) == 2:
-            query_points = query_points.unsqueeze(0)           # vggt.py:179-180
+        if query_points is not None:
+            if os.environ.get("IGGT_TRACK_HEAD", "0") != "1":
+                # the B200 track head is built (heads/track_head.py) but its correlation lookup has not been
+                # re-verified on a GPU since its last fix: opt in explicitly until it has
+                raise NotImplementedError("track_head (query_points) is experimental on the B200 path: set "
+                                          "IGGT_TRACK_HEAD=1 to enable it, or use the reference TrackHead on the "
+                                          "returned tokens")
+            if len(query_points.shape) == 2:
+                query_points = query_points.unsqueeze(0)       # vggt.py:179-180
         dt = self._dtype()
         tokens, psi = self.aggregator(images, compute_dtype=dt)
         predictions = {}

@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt"))
-                if not os.path.basename(p).startswith("postprocess"))
+                if os.path.basename(p).startswith(("iggt_", "vggt_")))      # the whole-forward fixtures (make_golden.py)
 L2_TOL = {"depth": 2e-3, "depth_conf": 2e-3, "world_points": 5e-3, "world_points_conf": 2e-3, "part_feat": 6e-3,
           "pose_enc": 5e-3}
 

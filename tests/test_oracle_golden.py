@@ -9,7 +9,7 @@ import torch
 from oracle import ref_model, weights
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt"))
-                if not os.path.basename(p).startswith("postprocess"))
+                if os.path.basename(p).startswith(("iggt_", "vggt_")))      # the whole-forward fixtures (make_golden.py)
 PREFIXES = ("aggregator.", "camera_head.", "depth_head.", "point_head.", "part_adaptor.", "part_head.")
 
 

@@ -1,6 +1,6 @@
 """The track-head oracle against the fixture produced by the unmodified reference
-(`VGGT.forward(images, query_points)`, oracle/make_golden_track.py).  CPU only; the B200 track head itself is not built
-yet - this pins the restatement it will be tested against."""
+(`VGGT.forward(images, query_points)`, oracle/make_golden_track.py).  CPU only: this pins the restatement that the B200
+track head (heads/track_head.py) is tested against in tests/test_track_wiring.py (CPU) and tests/test_track_gpu.py."""
 import os
 import sys
 

@@ -57,3 +57,12 @@ def test_track_module_wiring_teacher_forced(monkeypatch):
         assert (preds[i] - rec["track_all_iters"][i]).abs().max().item() < 2e-3        # pixels
     assert preds[-1].shape == rec["track"].shape and torch.equal(preds[-1][:, 0], rec["query_points"][None])
     assert (vis - rec["vis"]).abs().max().item() < 1e-4 and (conf - rec["conf"]).abs().max().item() < 1e-4
+
+
+def test_query_points_are_opt_in(monkeypatch):
+    """Until the correlation lookup has been re-verified on a GPU the track branch needs IGGT_TRACK_HEAD=1."""
+    import pytest
+    from iggt_official_b200.models.vggt import VGGT
+    monkeypatch.delenv("IGGT_TRACK_HEAD", raising=False)
+    with pytest.raises(NotImplementedError, match="IGGT_TRACK_HEAD=1"):
+        VGGT()(torch.zeros(2, 3, 28, 28), query_points=torch.zeros(3, 2))
