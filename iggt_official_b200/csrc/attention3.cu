@@ -5,7 +5,7 @@
 //   WG1,WG2 : softmax of query tile A, each thread owns HALF a query row (64 of the 128 keys of a kv tile)
 //   WG3,WG4 : softmax of query tile B                                                       (setmaxnreg.inc)
 // Four softmax warps per SM sub-partition hide the mbarrier / TMEM / MUFU latencies that left v2 (two per
-// sub-partition) at 50 % of the MUFU roofline (profiles/r01_ncu_attention_v2.md).
+// sub-partition) at 50 % of the MUFU roofline (profiles/r01_ncu_notes.md).
 // O accumulates in TMEM across kv tiles (tcgen05.mma accumulate); the running max is only refreshed -- and O
 // rescaled in TMEM (tcgen05.ld / tcgen05.st) -- when some row's max grows by more than 2^8 (lazy rescaling), so
 // the steady-state loop is: TMEM->reg S, max, exp2, pack, st.shared P.  Row halves agree on the max through a
@@ -545,9 +545,9 @@ extern "C" int iggt_attention_schedule(int num_seq, int Lq, int Lk, int H, int g
   return n;
 }
 
-extern "C" int iggt_attention_fwd_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                     int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
-                                     int head_dim, float scale, int dtype, iggt_stream_t stream) {
+extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                  int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
+                                  int head_dim, float scale, int dtype, iggt_stream_t stream) {
   if (head_dim != 64) return -1;
   if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return -1;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -2;

@@ -1,4 +1,4 @@
-"""Time the attention kernel variants (env IGGT_ATTN / IGGT_ATTN_EMU are read once per process)."""
+"""Time the attention kernel variants (env IGGT_ATTN_EMU / _PT / _STAG are read once per process)."""
 import json, os, subprocess, sys
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
@@ -23,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps(res))
 else:
     for ver, emu, pt, stag in [("3", "0", "1", "2"), ("3", "1", "1", "2")]:
-        env = dict(os.environ, IGGT_ATTN=ver, IGGT_ATTN_EMU=emu, IGGT_ATTN_PT=pt, IGGT_ATTN_STAG=stag)
+        env = dict(os.environ, IGGT_ATTN_EMU=emu, IGGT_ATTN_PT=pt, IGGT_ATTN_STAG=stag)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True,
                            cwd=os.path.dirname(os.path.abspath(__file__)), timeout=300)
         print(f"attn v{ver} emu{emu} pt{pt} stag{stag}:", r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-800:])
