@@ -101,3 +101,33 @@ def track_input(coords, fcorr, tfeat, pos, ref_tok, ln_w, ln_b, S, dtype, ldo=39
     out = torch.zeros(rows, ldo, dtype=dtype)
     out[:, :388] = F.layer_norm(x, (388,), ln_w, ln_b, 1e-5).to(dtype)
     return (out, x) if want_raw else out
+
+
+def corr_sample_direct(levels, targets, coords, B, N, S, ldo=576):
+    """The formulation csrc/track.cu uses, statement by statement: no correlation volume - <target, fmap> on the
+    10 x 10 integer pixels under each window (zero outside the level), then the bilinear combination; an axis that has
+    shrunk to one pixel pins the centre to 0 and freezes the window index (the reference's size-1 quirk).  Must equal
+    `corr_sample`, which samples the full volume the way the reference does."""
+    rows = B * N * S
+    out = torch.zeros((rows, ldo), dtype=levels[0].dtype)
+    img = (torch.arange(rows) // (N * S)) * S + torch.arange(rows) % S
+    k = torch.arange(100)
+    for l, fm in enumerate(levels):
+        _, H, W, C = fm.shape
+        flat_x, flat_y = W == 1, H == 1
+        cx = torch.zeros(rows) if flat_x else coords[:, 0] / (2 ** l)
+        cy = torch.zeros(rows) if flat_y else coords[:, 1] / (2 ** l)
+        fx0, fy0 = cx.floor(), cy.floor()
+        fx, fy = (cx - fx0)[:, None], (cy - fy0)[:, None]
+        px = (fx0.long() - 4)[:, None] + (k % 10)[None]                      # [rows, 100]
+        py = (fy0.long() - 4)[:, None] + (k // 10)[None]
+        ok = (px >= 0) & (px < W) & (py >= 0) & (py < H)
+        pix = fm.float()[img[:, None], py.clamp(0, H - 1), px.clamp(0, W - 1)]      # [rows, 100, C]
+        patch = torch.einsum("rc,rkc->rk", targets, pix) / math.sqrt(C) * ok
+        o = torch.arange(81)
+        i = torch.full((81,), 4) if flat_x else o // 9
+        j = torch.full((81,), 4) if flat_y else o % 9
+        q = j * 10 + i
+        v = (patch[:, q] * (1 - fx) + patch[:, q + 1] * fx) * (1 - fy) + (patch[:, q + 10] * (1 - fx) + patch[:, q + 11] * fx) * fy
+        out[:, l * 81:(l + 1) * 81] = v.to(out.dtype)
+    return out

@@ -66,3 +66,24 @@ def test_query_points_are_opt_in(monkeypatch):
     monkeypatch.delenv("IGGT_TRACK_HEAD", raising=False)
     with pytest.raises(NotImplementedError, match="IGGT_TRACK_HEAD=1"):
         VGGT()(torch.zeros(2, 3, 28, 28), query_points=torch.zeros(3, 2))
+
+
+def test_corr_lookup_without_the_volume_equals_volume_sampling():
+    """The kernel's formulation (dot products on the integer pixels under the window, interpolated afterwards) against
+    the reference's (sample the full correlation volume), down to 1 x 1, 1 x 2 and 2 x 1 pyramid levels."""
+    g = torch.Generator().manual_seed(2)
+    B, N, S = 1, 4, 2
+    rows = B * N * S
+    for h, w in ((70, 77), (64, 130), (130, 64)):
+        lv = [torch.randn(B * S, h, w, 128, generator=g)]
+        for _ in range(6):
+            lv.append(emu_ops.avgpool2_nhwc(lv[-1]))
+        targets = torch.randn(rows, 128, generator=g)
+        coords = torch.rand(rows, 2, generator=g) * torch.tensor([w + 3.0, h + 4.0]) - 2.0   # windows hang over every border
+        coords[0] = torch.tensor([0.0, 0.0])
+        coords[1] = torch.tensor([w - 1.0, h - 1.0])
+        a = emu_ops.corr_sample(lv, targets, coords, B, N, S)
+        b = emu_ops.corr_sample_direct(lv, targets, coords, B, N, S)
+        for lvl in range(7):
+            blk = slice(lvl * 81, (lvl + 1) * 81)
+            assert (a[:, blk] - b[:, blk]).abs().max().item() < 1e-4 * max(a[:, blk].abs().max().item(), 1e-3), (h, w, lvl)
