@@ -1,18 +1,22 @@
-// Flash-attention forward v3 for head_dim 64 on sm_100a.
+// Flash-attention forward for head_dim 64 on sm_100a (third generation of this kernel; the first two are in the git
+// history).  Replaces F.scaled_dot_product_attention at iggt/layers/attention.py:61-66.
 //
-// Persistent CTAs over (sequence, head, pair of 128-row query tiles), 20 warps:
-//   WG0     : warp 0 TMA producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator      (setmaxnreg.dec)
+// Persistent CTAs over work items (sequence, head, pair of 128-row query tiles A / B), 20 warps:
+//   WG0     : warp 0 TMA producer (Q double-buffered per tile, 3-stage K / V ring shared by both tiles),
+//             warps 1 and 3 one tcgen05.mma issuer thread per query tile, warp 2 TMEM allocator   (setmaxnreg.dec)
 //   WG1,WG2 : softmax of query tile A, each thread owns HALF a query row (64 of the 128 keys of a kv tile)
-//   WG3,WG4 : softmax of query tile B                                                       (setmaxnreg.inc)
-// Four softmax warps per SM sub-partition hide the mbarrier / TMEM / MUFU latencies that left v2 (two per
-// sub-partition) at 50 % of the MUFU roofline (profiles/r01_ncu_notes.md).
+//   WG3,WG4 : softmax of query tile B                                                               (setmaxnreg.inc)
+// Four softmax warps per SM sub-partition hide the mbarrier / TMEM / MUFU latencies that left the second generation
+// (two per sub-partition) at 50 % of the MUFU roofline (profiles/r01_ncu_notes.md).
 // O accumulates in TMEM across kv tiles (tcgen05.mma accumulate); the running max is only refreshed -- and O
-// rescaled in TMEM (tcgen05.ld / tcgen05.st) -- when some row's max grows by more than 2^8 (lazy rescaling), so
-// the steady-state loop is: TMEM->reg S, max, exp2, pack, st.shared P.  Row halves agree on the max through a
-// shared-memory exchange that only happens on a rescale; the decision is taken with one bar.red.or per tile.
+// rescaled in TMEM (tcgen05.ld / tcgen05.st) -- when some row's max grows by more than 2^8 (lazy rescaling), so the
+// steady-state loop is: TMEM->reg S, max, scale-and-shift (packed FFMA2), exp2 (MUFU), row sums (packed FADD2), pack
+// to 16 bit, tcgen05.st P.  P never touches shared memory: the PV MMA reads its A operand from TMEM (PT variant, the
+// default).  Row halves agree on the max through a shared-memory exchange that only happens on a rescale; the
+// decision is taken with one bar.red.or per tile.  Item schedule: Attn3Items below.
 //
 // TMEM map (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512)
-// (P: 128 keys x 16 bit = 64 columns per query row, only used by the PT variant)
+// (P: 128 keys x 16 bit = 64 columns per query row)
 #include <stdlib.h>
 #include "ptx.cuh"
 #include "tmap.cuh"
