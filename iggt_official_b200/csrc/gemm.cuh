@@ -2,10 +2,11 @@
 //
 //   D[M,N] = epilogue( A[M,K] (16-bit, K-major) x W[N,K]^T (16-bit, K-major), fp32 accumulate in TMEM )
 //
-// One CTA per SM loops over 128 x BN output tiles. Warp roles: warp 0 = TMA producer, warp 1 = MMA
-// issuer (one elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers ->
-// swizzled smem staging -> TMA store / TMA reduce-add). Two TMEM accumulator stages let the epilogue of
-// tile i overlap the main loop of tile i+1.
+// One CTA per SM loops over 128 x BN output tiles (or, PAIR, two CTAs of a cluster over 256 x BN tiles with one
+// cta_group::2 MMA). Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
+// allocator, warps 4.. = one or two 4-warp epilogue groups (TMEM -> registers -> swizzled smem staging -> TMA store /
+// TMA reduce-add). Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1; work is
+// handed out by WorkIter (whole tiles round-robin, or stream-K ranges of k-blocks for the residual epilogue).
 //
 // Reference call sites this replaces (all via torch.nn on the reference side):
 //   qkv   iggt/layers/attention.py:52-58   (+ q/k LayerNorm(64) and 2-D RoPE, rope.py:154-188)
