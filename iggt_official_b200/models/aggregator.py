@@ -69,6 +69,13 @@ def token_positions(gh: int, gw: int, device) -> torch.Tensor:
     return torch.cat([torch.zeros(NUM_SPECIAL, 2, dtype=p.dtype, device=device), p], 0).int().contiguous()
 
 
+def _require_cuda(images: torch.Tensor):
+    """The product path has no CPU fallback.  (tests/test_model_wiring.py replaces this hook AND every launcher of
+    `ops` with PyTorch statements to exercise the host-side graph on the CPU.)"""
+    if not images.is_cuda:
+        raise RuntimeError("iggt_official_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
 class Aggregator(Node):
     def __init__(self):
         super().__init__()
@@ -158,8 +165,7 @@ class Aggregator(Node):
         if C_in != 3:
             raise ValueError(f"Expected 3 input channels, got {C_in}")                 # aggregator.py:202-203
         assert H % PATCH == 0 and W % PATCH == 0, "Input image size must be a multiple of the patch size"
-        if not images.is_cuda:
-            raise RuntimeError("iggt_official_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        _require_cuda(images)
         dt = compute_dtype or (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16)
         dev = images.device
         pk = self._packed(dt, dev)

@@ -131,3 +131,162 @@ def corr_sample_direct(levels, targets, coords, B, N, S, ldo=576):
         v = (patch[:, q] * (1 - fx) + patch[:, q + 1] * fx) * (1 - fy) + (patch[:, q + 10] * (1 - fx) + patch[:, q + 11] * fx) * fy
         out[:, l * 81:(l + 1) * 81] = v.to(out.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Statements of the trunk / DPT / camera-head launchers (same formulas as the references in
+# tests/test_kernels_gpu.py), used by tests/test_model_wiring.py to run the module graph on the CPU.
+def _act(v, act):
+    if act == 1:
+        return F.gelu(v)
+    if act == 2:
+        return F.relu(v)
+    if act == 3:
+        return F.leaky_relu(v, 0.01)
+    if act == 4:
+        return F.silu(v)
+    return v
+
+
+def gemm_store16_full(a, w, bias=None, act=0, addend=None, add_rows=0, out=None):
+    v = a.float() @ w.float().t()
+    if bias is not None:
+        v = v + bias
+    if act == 1:
+        v = v.to(a.dtype).float()                       # autocast: GELU sees the 16-bit Linear output
+    v = _act(v, act)
+    if addend is not None:
+        v = v + addend.float().repeat(v.shape[0] // add_rows, 1)
+    return v.to(a.dtype)
+
+
+def gemm_resid32_full(a, w, x, bias=None, gamma=None, round_out16=False):
+    v = a.float() @ w.float().t()
+    if bias is not None:
+        v = v + bias
+    if round_out16:
+        v = v.to(a.dtype).float()
+    x += v if gamma is None else v * gamma
+    return x
+
+
+def layernorm(x, w, b, eps, out, groups=None, rows_out=None, rows_in=None, in_off=0, out_rows_per_group=None, out_off=0):
+    C = x.shape[1]
+    if groups is None:
+        groups, rows_out, rows_in = 1, x.shape[0], x.shape[0]
+    if out_rows_per_group is None:
+        out_rows_per_group = rows_out
+    src = x.reshape(-1, C)[:groups * rows_in].view(groups, rows_in, C)[:, in_off:in_off + rows_out]
+    y = F.layer_norm(src, (C,), w, b, eps)
+    out.view(-1, out.shape[-1])[:groups * out_rows_per_group].view(groups, out_rows_per_group, -1)[
+        :, out_off:out_off + rows_out, :C] = y.to(out.dtype)
+    return out
+
+
+def _rope(t, pos, cos16, sin16):
+    """t [M, heads, 64]; pos [M, 2] (y, x); dims [0,32) rotate with y, [32,64) with x; rotate-half of 16."""
+    def one(x, p):
+        c = torch.cat([cos16[p], cos16[p]], -1)[:, None, :]
+        s = torch.cat([sin16[p], sin16[p]], -1)[:, None, :]
+        rot = torch.cat([-x[..., 16:], x[..., :16]], -1)
+        return x * c + rot * s
+    return torch.cat([one(t[..., :32], pos[:, 0]), one(t[..., 32:], pos[:, 1])], -1)
+
+
+def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b=None, rope_cos=None, rope_sin=None,
+             pos_yx=None, T=0, out=None, **_):
+    v = a.float() @ w.float().t() + bias
+    if qk_norm:
+        M = v.shape[0]
+        v = v.to(a.dtype).float()
+        q, k, vv = v.view(M, 3, C // 64, 64).unbind(1)
+        q = F.layer_norm(q, (64,), qn_w, qn_b, 1e-5)
+        k = F.layer_norm(k, (64,), kn_w, kn_b, 1e-5)
+        pos = pos_yx.long().repeat(M // T, 1)
+        q, k = _rope(q, pos, rope_cos, rope_sin), _rope(k, pos, rope_cos, rope_sin)
+        v = torch.stack([q, k, vv], 1).reshape(M, 3 * C)
+    return v.to(a.dtype)
+
+
+def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None, act_post=0):
+    NB, H, W, Cin = x.shape
+    Cout = wp.shape[0]
+    ks = 3 if taps == 9 else 1
+    w = wp.float().view(Cout, ks, ks, Cin).permute(0, 3, 1, 2)
+    v = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=ks // 2).permute(0, 2, 3, 1)
+    v = _act(v, act)
+    if resid is not None:
+        v = v + resid.float()
+    if resid2 is not None:
+        v = v + resid2.float()
+    return _act(v, act_post).to(x.dtype).contiguous()
+
+
+def upsample_bilinear(x, H, W, tabx=None, taby=None, out=None):
+    NB, h, w, C = x.shape
+    v = F.interpolate(x.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    if tabx is not None:
+        v = v + torch.cat([tabx[None, None].expand(NB, H, W, C // 2), taby[None, :, None].expand(NB, H, W, C // 2)], -1)
+    return v.to(x.dtype).contiguous()
+
+
+def deconv_shuffle(y, NB, h, w, C, k):
+    return y.view(NB, h, w, k, k, C).permute(0, 1, 3, 2, 4, 5).reshape(NB, h * k, w * k, C).contiguous()
+
+
+def im2col3x3_s2(x):
+    NB, h, w, C = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), kernel_size=3, stride=2, padding=1)          # [NB, C*9, ho*wo]
+    A = cols.view(NB, C, 9, ho * wo).permute(0, 3, 2, 1).reshape(NB * ho * wo, 9 * C)           # tap-major, then channel
+    return A.to(x.dtype).contiguous(), ho, wo
+
+
+def dpt_tail(x, w, b, mode):
+    o = x.float() @ w.t() + b
+    if mode == 2:
+        return o.permute(0, 3, 1, 2).contiguous(), None
+    xyz = o[..., :-1]
+    main = torch.exp(xyz) if mode == 0 else torch.sign(xyz) * torch.expm1(xyz.abs())
+    return main.contiguous(), (1 + o[..., -1].exp()).contiguous()
+
+
+def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
+    v = x @ w.float().t()
+    if bias is not None:
+        v = v + bias
+    v = _act(v, act)
+    if gamma is not None:
+        v = v * gamma
+    if resid is not None:
+        v = v + resid
+    return v
+
+
+def small_attention(qkv, B, N, H, d):
+    q, k, v = qkv.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    return (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).transpose(1, 2).reshape(B * N, H * d)
+
+
+def patchify(images, KP, dtype):
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    cols = F.unfold((images - mean) / std, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    A = torch.zeros(cols.shape[0], KP, dtype=dtype)
+    A[:, :588] = cols.to(dtype)
+    return A
+
+
+def dino_assemble(pe16, cls, reg, pos, x, NI, P, R, C):
+    x.view(NI, 1 + R + P, C).copy_(torch.cat([(cls + pos[0]).expand(NI, 1, C), reg.expand(NI, R, C),
+                                              pe16.float().view(NI, P, C) + pos[1:]], 1))
+    return x
+
+
+def special_tokens(cam, reg, x, NI, T, R, C, S_loc, view_offset):
+    xv = x.view(NI, T, C)
+    for n in range(NI):
+        var = 0 if (view_offset + n % S_loc) == 0 else 1
+        xv[n, 0] = cam[var]
+        xv[n, 1:1 + R] = reg[var]
+    return x
