@@ -290,3 +290,60 @@ def special_tokens(cam, reg, x, NI, T, R, C, S_loc, view_offset):
         xv[n, 0] = cam[var]
         xv[n, 1:1 + R] = reg[var]
     return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# Part path (csrc/part.cu)
+def col2im_k4s2p1(y, bias, NB, h, w, C):
+    """y [NB*h*w, 16*C] with column (dy*4+dx)*C + co (ConvTranspose2d k=4, s=2, p=1 as GEMM) -> [NB, 2h, 2w, C] + bias."""
+    cols = y.float().view(NB, h * w, 16, C).permute(0, 3, 2, 1).reshape(NB, C * 16, h * w)
+    out = F.fold(cols, output_size=(2 * h, 2 * w), kernel_size=4, stride=2, padding=1)
+    return (out + bias.view(1, C, 1, 1)).permute(0, 2, 3, 1).to(y.dtype).contiguous()
+
+
+def _window_partition(x, ws):                        # [B,H,W,C] -> [B*nw, ws, ws, C]
+    B, H, W, C = x.shape
+    return x.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, C)
+
+
+def _window_reverse(win, ws, H, W):
+    B = win.shape[0] // ((H // ws) * (W // ws))
+    return win.view(B, H // ws, W // ws, ws, ws, -1).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+def ocab_attention(q, k, v, table, rpi):
+    """OCAB window cross-attention: the same window math as the reference in tests/test_kernels_gpu.py (q windows come
+    from `window_partition` applied to the CHANNELS-FIRST map, i.e. the reference's scrambled gather)."""
+    b, h, w, c = q.shape
+    ws, heads = 8, 4
+    qf, kf, vf = (t.float().permute(0, 3, 1, 2) for t in (q, k, v))
+    q_win = _window_partition(qf, ws).reshape(-1, ws * ws, c)
+    kvw = F.unfold(torch.cat([kf, vf], 1), kernel_size=(12, 12), stride=ws, padding=2)
+    nw = kvw.shape[-1]
+    kvw = kvw.view(b, 2, c, 144, nw).permute(1, 0, 4, 3, 2).reshape(2, b * nw, 144, c)
+    d = c // heads
+    qh = q_win.reshape(-1, 64, heads, d).permute(0, 2, 1, 3) * d ** -0.5
+    kh = kvw[0].reshape(-1, 144, heads, d).permute(0, 2, 1, 3)
+    vh = kvw[1].reshape(-1, 144, heads, d).permute(0, 2, 1, 3)
+    bias = table[rpi.long().view(-1)].view(64, 144, -1).permute(2, 0, 1)
+    att = torch.softmax(qh @ kh.transpose(-2, -1) + bias.unsqueeze(0), -1)
+    o = (att @ vh).transpose(1, 2).reshape(-1, 64, c).view(-1, ws, ws, c)
+    return _window_reverse(o, ws, h, w).to(q.dtype).contiguous()
+
+
+def window_attention(qkv):
+    b, h, w, c3 = qkv.shape
+    c, heads = c3 // 3, 4
+    xw = _window_partition(qkv.float(), 8).view(-1, 64, 3, heads, c // heads).transpose(1, 3)
+    q, k, v = xw[:, :, 0], xw[:, :, 1], xw[:, :, 2]
+    o = (torch.softmax(q @ k.transpose(-2, -1) * (c // heads) ** -0.5, -1) @ v).transpose(1, 2).reshape(-1, 64, c)
+    return _window_reverse(o.view(-1, 8, 8, c), 8, h, w).to(qkv.dtype).contiguous()
+
+
+def channel_mean(x):
+    return x.float().mean((1, 2))
+
+
+def se_scale_add(y0, cx, mean, w1, b1, w2, b2, alpha):
+    s = torch.sigmoid(F.relu(mean @ w1.t() + b1) @ w2.t() + b2)
+    return (y0.float() + alpha * cx.float() * s[:, None, None, :]).to(y0.dtype)

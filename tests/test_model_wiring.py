@@ -16,29 +16,31 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import emu_ops                                                              # noqa: E402
 from oracle import weights                                                  # noqa: E402
 
-FIX = os.path.join(ROOT, "tests", "golden", "vggt_s2_42x42_stress.pt")
 EMU = {"gemm_store16": emu_ops.gemm_store16_full, "gemm_store32": emu_ops.gemm_store32, "gemm_resid32": emu_ops.gemm_resid32_full,
        "gemm_qkv": emu_ops.gemm_qkv, "attention": emu_ops.attention, "layernorm": emu_ops.layernorm,
        "layernorm16": emu_ops.layernorm16, "conv_nhwc": emu_ops.conv_nhwc, "upsample_bilinear": emu_ops.upsample_bilinear,
        "deconv_shuffle": emu_ops.deconv_shuffle, "im2col3x3_s2": emu_ops.im2col3x3_s2, "dpt_tail": emu_ops.dpt_tail,
        "skinny_gemm": emu_ops.skinny_gemm, "small_attention": emu_ops.small_attention, "patchify": emu_ops.patchify,
-       "dino_assemble": emu_ops.dino_assemble, "special_tokens": emu_ops.special_tokens}
+       "dino_assemble": emu_ops.dino_assemble, "special_tokens": emu_ops.special_tokens,
+       "col2im_k4s2p1": emu_ops.col2im_k4s2p1, "ocab_attention": emu_ops.ocab_attention,
+       "window_attention": emu_ops.window_attention, "channel_mean": emu_ops.channel_mean, "se_scale_add": emu_ops.se_scale_add}
 
 
 def _l2(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
 
 
-def test_vggt_graph_with_emulated_launchers_matches_reference_fixture(monkeypatch):
+@pytest.mark.parametrize("fixture", ["vggt_s2_42x42_stress", "iggt_s2_28x56_stress", "iggt_b2s3_28x28_default"])
+def test_model_graph_with_emulated_launchers_matches_reference_fixture(monkeypatch, fixture):
     from iggt_official_b200 import ops
     from iggt_official_b200.models import aggregator as agg_mod
-    from iggt_official_b200.models.vggt import VGGT
+    from iggt_official_b200.models.vggt import IGGT, VGGT
     for name, fn in EMU.items():
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(agg_mod, "_require_cuda", lambda images: None)
-    rec = torch.load(FIX)
+    rec = torch.load(os.path.join(ROOT, "tests", "golden", fixture + ".pt"))
     c = rec["case"]
-    m = VGGT()
+    m = (IGGT if c["model"] == "IGGT" else VGGT)()
     m.load_state_dict(weights.make_state_dict(c["wseed"], c["kind"]), strict=False)
     m.eval()
     m.compute_dtype = torch.float32                                          # "16-bit" operands kept exact
@@ -46,7 +48,7 @@ def test_vggt_graph_with_emulated_launchers_matches_reference_fixture(monkeypatc
     images = torch.rand(c["B"], c["S"], 3, c["H"], c["W"], generator=g)
     out = m(images[0] if c["B"] == 1 else images)
     assert _l2(torch.stack(out["pose_enc"]), rec["pose_enc"]) < 1e-4
-    for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
+    for k in ("depth", "depth_conf", "world_points", "world_points_conf") + (("part_feat",) if c["model"] == "IGGT" else ()):
         assert out[k].shape == rec[k].shape, k
         assert _l2(out[k], rec[k]) < 1e-4, (k, _l2(out[k], rec[k]))
 
