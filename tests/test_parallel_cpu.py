@@ -43,3 +43,51 @@ def test_view_shard_gathers(B, S_loc, T):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), B, S_loc, T, ret), nprocs=world, join=True)
     assert ret[0] and ret[1]
+
+
+def _sharded_worker(rank, world, port, ret):
+    """The whole view-sharded forward on the CPU: gloo collectives + the launchers replaced by their PyTorch statements
+    (tests/emu_ops.py).  Every rank also runs the unsharded forward and compares its own views."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(8)
+    import emu_ops
+    from test_model_wiring import EMU
+    from iggt_official_b200 import ops
+    from iggt_official_b200.models import aggregator as agg_mod
+    from iggt_official_b200.models.vggt import VGGT
+    from iggt_official_b200.parallel import forward_sharded
+    for name, fn in EMU.items():
+        setattr(ops, name, fn)
+    agg_mod._require_cuda = lambda images: None
+    torch.manual_seed(0)                                   # identical random-init weights on every rank
+    m = VGGT().eval()
+    m.compute_dtype = torch.float32
+    g = torch.Generator().manual_seed(3)
+    B, S, H, W = 2, 4, 28, 42
+    images = torch.rand(B, S, 3, H, W, generator=g)
+    S_loc = S // world
+    mine = images[:, rank * S_loc:(rank + 1) * S_loc].contiguous()
+    out = forward_sharded(m, mine, rank, world)
+    m.aggregator.process_group = None
+    ref = m(images)
+    ok = True
+    for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
+        a, b = out[k], ref[k][:, rank * S_loc:(rank + 1) * S_loc]
+        ok = ok and a.shape == b.shape and ((a - b).abs().max() / b.abs().max()).item() < 1e-5
+    pe = (torch.stack(out["pose_enc"]) - torch.stack(ref["pose_enc"])).abs().max().item()
+    ret[rank] = bool(ok and pe < 1e-5)
+    dist.destroy_process_group()
+
+
+def test_view_sharded_forward_equals_unsharded_forward():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
