@@ -172,7 +172,7 @@ def run_b200(args):
     if not args.no_graph and not args.quick:
         from iggt_official_b200.graphs import GraphedForward
         try:
-            g_step = GraphedForward(eager_step)
+            g_step = GraphedForward(eager_step, model=model)
             g_step(images_dev)                     # capture now; fall back to eager launches if it fails
             torch.cuda.synchronize()
             step, graphed = g_step, True

@@ -500,16 +500,12 @@ template <bool BF16, int EMU, bool PT>
 int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const Attn3Params& p,
                       cudaStream_t stream) {
   auto kern = attention3_kernel<BF16, EMU, PT>;
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    if (e != cudaSuccess) { once.reset_current(); return (int)e; }
   }
+  const int sms = device_sm_count();
   const int grid = p.total_items < sms ? p.total_items : sms;
   return (int)launch_pdl(kern, dim3(grid), dim3(A3_THREADS), A3_SMEM, stream, tQ, tK, tV, p);
 }

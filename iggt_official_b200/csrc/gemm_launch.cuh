@@ -5,17 +5,6 @@
 
 namespace iggt {
 
-inline int device_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 // Pick the N tile: fewest "wave-quantised" tile-slots; ties go to the wider tile (less smem traffic
 // per MAC: a 128x256 tile reads 96 B/clk of operands, 128x128 reads 128 B/clk).
 inline int choose_bn(int m_tiles, int N) {
@@ -91,13 +80,12 @@ template <int BN, int EPI, bool BF16, bool CONV, bool PAIR = false, int G = (EPI
 inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                               const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BN, EPI, BF16, CONV, G, PAIR>;
-  static bool configured = false;
+  static DeviceOnce once;
   constexpr int smem = GemmSmem<BN, PAIR>::TOTAL;
   static_assert(smem <= 232448, "shared memory budget");
-  if (!configured) {
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+    if (e != cudaSuccess) { once.reset_current(); return (int)e; }
   }
   const int workers_max = PAIR ? device_sm_count() / 2 : device_sm_count();
   const int tiles = p.num_m_tiles * p.num_n_tiles;

@@ -366,11 +366,10 @@ extern "C" int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int6
   if (M <= 0 || M > 32 || N <= 0 || K <= 0 || (K % 8) || (ldx % 4) || (ldw % 8)) return -1;
   const unsigned grid = (N + SK_COLS - 1) / SK_COLS;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
     cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
-    configured = true;
   }
   CUtensorMap tW;
   {
@@ -399,10 +398,9 @@ extern "C" int iggt_small_attention(const float* qkv, float* out, int B, int N, 
   if (B <= 0 || N <= 0 || N > 256 || H <= 0 || d <= 0) return -1;
   const size_t smem = (2 * static_cast<size_t>(N) * d + 4 * N) * sizeof(float);
   if (smem > 200 * 1024) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
   }
   small_attention_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>(qkv, out, N, H, d, scale);
   return (int)cudaGetLastError();

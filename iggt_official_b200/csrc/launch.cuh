@@ -13,6 +13,40 @@ namespace iggt {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Per-device caches (a second device in the same process must get its own cudaFuncSetAttribute opt-in and
+// its own SM count).  kMaxDevices bounds the tables; an out-of-range ordinal is simply never cached.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+// `static DeviceOnce once; if (once.first()) { ...configure the kernel on the current device... }`
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (d < 0 || d >= kMaxDevices) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+  void reset_current() {          // configuration failed: try again at the next launch
+    const int d = current_device();
+    if (d >= 0 && d < kMaxDevices) done[d] = false;
+  }
+};
+inline int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int d = current_device();
+  if (d < 0 || d >= kMaxDevices) return 148;
+  if (!n[d]) {
+    cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+    if (n[d] <= 0) n[d] = 148;
+  }
+  return n[d];
+}
+
 inline int pdl_enabled() {
   static const int v = [] { const char* e = getenv("IGGT_PDL"); return e ? atoi(e) : 1; }();
   return v;

@@ -4,6 +4,7 @@
 // HAB plain window self-attention), and the CAB channel-attention (squeeze-excite) pieces.
 // Reference: iggt/heads/adaptor.py:140-226, iggt/heads/part_head.py:148-243, iggt/heads/window_sa.py.
 #include "ptx.cuh"
+#include "launch.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -411,11 +412,10 @@ extern "C" int iggt_col2im_k4s2p1(const void* Y, const float* bias, void* out, i
 extern "C" int iggt_ocab_attention(const void* q, const void* k, const void* v, const float* table, const int* rpi,
                                    void* out, int NB, int h, int w, int dtype, iggt_stream_t stream) {
   if (NB <= 0 || (h % 8) || (w % 8)) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(ocab_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OCAB_SMEM);
     cudaFuncSetAttribute(ocab_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OCAB_SMEM);
-    configured = true;
   }
   const unsigned grid = static_cast<unsigned>(NB) * (h / 8) * (w / 8) * 4;
   if (dtype) ocab_attention_kernel<true><<<grid, 256, OCAB_SMEM, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, table, rpi, (uint16_t*)out, h, w);

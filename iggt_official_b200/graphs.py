@@ -14,12 +14,24 @@ class GraphedForward:
     """Wraps `fn(images) -> dict of tensors / lists of tensors`.  One graph per (shape, dtype) of `images`.
     Outputs are static buffers that the next replay overwrites (copy them if they must survive)."""
 
-    def __init__(self, fn: Callable, warmup: int = 2):
+    def __init__(self, fn: Callable, warmup: int = 2, model=None):
+        """`model` (an IGGT / VGGT module): its weight-pack generation becomes part of the graph key, so graphs captured
+        before a `load_state_dict()` / `.to()` / `invalidate_packed()` - whose packed 16-bit weights have been freed -
+        are never replayed; they are dropped and re-captured on the next call."""
         self.fn = fn
         self.warmup = warmup
+        self.model = model
         self._graphs: Dict[Tuple, Tuple] = {}
+        self._generation = self._gen()
+
+    def _gen(self):
+        return getattr(self.model, "_pack_generation", 0) if self.model is not None else 0
 
     def __call__(self, images: torch.Tensor):
+        gen = self._gen()
+        if gen != self._generation:            # weights were re-packed: every captured graph points at freed memory
+            self._graphs.clear()
+            self._generation = gen
         key = (tuple(images.shape), images.dtype, images.device.index)
         if key not in self._graphs:
             self._graphs[key] = self._capture(images)

@@ -11,11 +11,9 @@ Differences from the reference that a caller can observe:
   * CUDA only (no CPU fallback); the 16-bit compute dtype follows the enclosing autocast (fp16 when there is
     none -- the reference would run fp32).
   * S > 12 views works (the reference's frame-chunk path raises TypeError).
-  * `query_points` (track head) is implemented (heads/track_head.py) but stays opt-in
-    (IGGT_TRACK_HEAD=1) until its last kernel fix has been re-verified on a GPU; without the opt-in it raises
-    NotImplementedError as before.
+  * `query_points` runs the B200 track head (heads/track_head.py, reference iggt/models/vggt.py:220-226) and adds
+    `track`, `vis`, `conf` to the dictionary exactly like the reference; S > 12 works there too.
 """
-import os
 from typing import Optional
 
 import torch
@@ -54,7 +52,10 @@ class _Base(nn.Module, PyTorchModelHubMixin):
         self.compute_dtype: Optional[torch.dtype] = None     # None: follow autocast, else fp16
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
+    _pack_generation = 0
+
     def invalidate_packed(self):
+        self._pack_generation += 1             # graphs.GraphedForward keys its captured graphs on this
         for m in self.modules():
             if m is not self and hasattr(m, "invalidate"):
                 m.invalidate()
@@ -74,12 +75,6 @@ class _Base(nn.Module, PyTorchModelHubMixin):
         if len(images.shape) == 4:
             images = images.unsqueeze(0)
         if query_points is not None:
-            if os.environ.get("IGGT_TRACK_HEAD", "0") != "1":
-                # the B200 track head is built (heads/track_head.py) but its correlation lookup has not been
-                # re-verified on a GPU since its last fix: opt in explicitly until it has
-                raise NotImplementedError("track_head (query_points) is experimental on the B200 path: set "
-                                          "IGGT_TRACK_HEAD=1 to enable it, or use the reference TrackHead on the "
-                                          "returned tokens")
             if len(query_points.shape) == 2:
                 query_points = query_points.unsqueeze(0)       # vggt.py:179-180
         dt = self._dtype()

@@ -22,6 +22,13 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class _StreamArg:
+    """placeholder for "the current stream of the launch device", resolved inside _call (after the device switch)"""
+
+
+_STREAM = _StreamArg()
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -40,7 +47,15 @@ STATS = {"launches": 0}
 TRACE = None
 
 
-def _call(name, flops, nbytes, *args):
+def _call(ref, name, flops, nbytes, *args):
+    """Launch C-ABI entry point `name` on the device that owns `ref` (one of the launch's tensors) and on that device's
+    current stream: `model.to("cuda:1")` works without `torch.cuda.set_device(1)`, like the reference's torch modules."""
+    if not ref.is_cuda:
+        raise RuntimeError(f"{name}: expected CUDA tensors (there is no CPU fallback on this path)")
+    if ref.device.index != torch.cuda.current_device():
+        with torch.cuda.device(ref.device):
+            return _call(ref, name, flops, nbytes, *args)
+    args = [(_stream() if a is _STREAM else a) for a in args]
     fn = getattr(_lib.load(), name)
     STATS["launches"] += 1
     if TRACE is None:
@@ -63,11 +78,11 @@ def gemm_store16(a, w, bias=None, act=0, addend=None, add_rows=0, out=None):
     if out is None:
         out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     _chk2d(out)
-    _call("iggt_gemm_store16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N),
+    _call(a, "iggt_gemm_store16", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N),
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                        out.stride(0), M, N, K, _dt(a), _ptr(bias), act, _ptr(addend),
                                        add_rows if addend is not None else 0,
-                                       addend.stride(0) if addend is not None else 0, _stream())
+                                       addend.stride(0) if addend is not None else 0, _STREAM)
     return out
 
 
@@ -77,9 +92,9 @@ def gemm_store32(a, w, bias=None, act=0, out=None):
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    _call("iggt_gemm_store32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N,
+    _call(a, "iggt_gemm_store32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N,
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
-                                       out.stride(0), M, N, K, _dt(a), _ptr(bias), act, _stream())
+                                       out.stride(0), M, N, K, _dt(a), _ptr(bias), act, _STREAM)
     return out
 
 
@@ -89,10 +104,10 @@ def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
     assert x.dtype == torch.float32
     M, K = a.shape
     N = w.shape[0]
-    _call("iggt_gemm_resid32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 8.0 * M * N,
+    _call(a, "iggt_gemm_resid32", 2.0 * M * N * K, 2.0 * (M * K + N * K) + 8.0 * M * N,
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(),
                                        x.stride(0), M, N, K, _dt(a), _ptr(bias), _ptr(gamma),
-                                       1 if round_out16 else 0, _stream())
+                                       1 if round_out16 else 0, _STREAM)
     return x
 
 
@@ -102,11 +117,11 @@ def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b
     M, K = a.shape
     if out is None:
         out = torch.empty((M, 3 * C), dtype=a.dtype, device=a.device)
-    _call("iggt_gemm_qkv", 6.0 * M * C * K, 2.0 * (M * K + 3 * C * K + 3 * M * C),
+    _call(a, "iggt_gemm_qkv", 6.0 * M * C * K, 2.0 * (M * K + 3 * C * K + 3 * M * C),
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, C, K, _dt(a), _ptr(bias), 1 if qk_norm else 0,
                                    _ptr(qn_w), _ptr(qn_b), _ptr(kn_w), _ptr(kn_b), _ptr(rope_cos),
-                                   _ptr(rope_sin), _ptr(pos_yx), T, _stream())
+                                   _ptr(rope_sin), _ptr(pos_yx), T, _STREAM)
     return out
 
 
@@ -120,9 +135,9 @@ def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None
         out = torch.empty((NB, H, W, Cout), dtype=x.dtype, device=x.device)
     if resid is not None:
         assert resid.shape == out.shape and resid.is_contiguous()
-    _call("iggt_conv_nhwc", 2.0 * NB * H * W * Cout * taps * Cin, 2.0 * (NB * H * W * (Cin + Cout) + Cout * taps * Cin),
+    _call(x, "iggt_conv_nhwc", 2.0 * NB * H * W * Cout * taps * Cin, 2.0 * (NB * H * W * (Cin + Cout) + Cout * taps * Cin),
           x.data_ptr(), wp.data_ptr(), out.data_ptr(), NB, H, W, Cin, Cout, taps,
-                                    _dt(x), _ptr(bias), act, _ptr(resid), _ptr(resid2), act_post, _stream())
+                                    _dt(x), _ptr(bias), act, _ptr(resid), _ptr(resid2), act_post, _STREAM)
     return out
 
 
@@ -132,10 +147,10 @@ def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None):
         _chk2d(t)
     if out is None:
         out = torch.empty((num_seq * Lq, H * 64), dtype=q.dtype, device=q.device)
-    _call("iggt_attention_fwd", 4.0 * num_seq * Lq * Lk * H * 64, 2.0 * num_seq * H * 64 * (2 * Lq + 2 * Lk),
+    _call(q, "iggt_attention_fwd", 4.0 * num_seq * Lq * Lk * H * 64, 2.0 * num_seq * H * 64 * (2 * Lq + 2 * Lk),
           q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
                                         v.stride(0), out.data_ptr(), out.stride(0), num_seq, Lq, Lk, H, 64,
-                                        float(scale), _dt(q), _stream())
+                                        float(scale), _dt(q), _STREAM)
     return out
 
 
@@ -152,10 +167,10 @@ def layernorm(x, w, b, eps, out, groups=None, rows_out=None, rows_in=None, in_of
         groups, rows_out, rows_in = 1, x.shape[0], x.shape[0]
     if out_rows_per_group is None:
         out_rows_per_group = rows_out
-    _call("iggt_layernorm", 0, groups * rows_out * C * (4 + out.element_size()),
+    _call(x, "iggt_layernorm", 0, groups * rows_out * C * (4 + out.element_size()),
           x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), C, _ptr(w),
                                     _ptr(b), float(eps), groups, rows_out, rows_in, in_off,
-                                    out_rows_per_group, out_off, _KIND[out.dtype], _stream())
+                                    out_rows_per_group, out_off, _KIND[out.dtype], _STREAM)
     return out
 
 
@@ -164,22 +179,22 @@ def patchify(images, KP, dtype):
     assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
     NI, _, H, W = images.shape
     A = torch.empty((NI * (H // 14) * (W // 14), KP), dtype=dtype, device=images.device)
-    _call("iggt_patchify", 0, images.numel() * 4 + A.numel() * 2,
-          images.data_ptr(), A.data_ptr(), NI, H, W, KP, _KIND[dtype], _stream())
+    _call(images, "iggt_patchify", 0, images.numel() * 4 + A.numel() * 2,
+          images.data_ptr(), A.data_ptr(), NI, H, W, KP, _KIND[dtype], _STREAM)
     return A
 
 
 def dino_assemble(pe16, cls, reg, pos, x, NI, P, R, C):
-    _call("iggt_dino_assemble", 0, x.numel() * 4 + pe16.numel() * 2,
+    _call(pe16, "iggt_dino_assemble", 0, x.numel() * 4 + pe16.numel() * 2,
           pe16.data_ptr(), cls.data_ptr(), reg.data_ptr(), pos.data_ptr(),
-                                        x.data_ptr(), NI, P, R, C, _dt(pe16), _stream())
+                                        x.data_ptr(), NI, P, R, C, _dt(pe16), _STREAM)
     return x
 
 
 def special_tokens(cam, reg, x, NI, T, R, C, S_loc, view_offset):
-    _call("iggt_special_tokens", 0, NI * (1 + R) * C * 4,
+    _call(cam, "iggt_special_tokens", 0, NI * (1 + R) * C * 4,
           cam.data_ptr(), reg.data_ptr(), x.data_ptr(), NI, T, R, C, S_loc,
-                                         view_offset, _stream())
+                                         view_offset, _STREAM)
     return x
 
 
@@ -189,16 +204,16 @@ def upsample_bilinear(x, H, W, tabx=None, taby=None, out=None):
     NB, h, w, C = x.shape
     if out is None:
         out = torch.empty((NB, H, W, C), dtype=x.dtype, device=x.device)
-    _call("iggt_upsample_bilinear_nhwc", 0, 2.0 * (x.numel() + out.numel()),
+    _call(x, "iggt_upsample_bilinear_nhwc", 0, 2.0 * (x.numel() + out.numel()),
           x.data_ptr(), out.data_ptr(), NB, h, w, H, W, C, _ptr(tabx),
-                                                 _ptr(taby), _dt(x), _stream())
+                                                 _ptr(taby), _dt(x), _STREAM)
     return out
 
 
 def deconv_shuffle(y, NB, h, w, C, k):
     out = torch.empty((NB, h * k, w * k, C), dtype=y.dtype, device=y.device)
-    _call("iggt_deconv_shuffle", 0, 4.0 * y.numel(),
-          y.data_ptr(), out.data_ptr(), NB, h, w, C, k, _stream())
+    _call(y, "iggt_deconv_shuffle", 0, 4.0 * y.numel(),
+          y.data_ptr(), out.data_ptr(), NB, h, w, C, k, _STREAM)
     return out
 
 
@@ -206,8 +221,8 @@ def im2col3x3_s2(x):
     NB, h, w, C = x.shape
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     A = torch.empty((NB * ho * wo, 9 * C), dtype=x.dtype, device=x.device)
-    _call("iggt_im2col3x3_s2", 0, 2.0 * (x.numel() + A.numel()),
-          x.data_ptr(), A.data_ptr(), NB, h, w, C, _stream())
+    _call(x, "iggt_im2col3x3_s2", 0, 2.0 * (x.numel() + A.numel()),
+          x.data_ptr(), A.data_ptr(), NB, h, w, C, _STREAM)
     return A, ho, wo
 
 
@@ -221,9 +236,9 @@ def dpt_tail(x, w, b, mode):
     else:
         main = torch.empty((NB, H, W, OC - 1), dtype=torch.float32, device=x.device)
         conf = torch.empty((NB, H, W), dtype=torch.float32, device=x.device)
-    _call("iggt_dpt_tail", 2.0 * NB * H * W * 32 * OC, NB * H * W * (64 + 4 * OC),
+    _call(x, "iggt_dpt_tail", 2.0 * NB * H * W * 32 * OC, NB * H * W * (64 + 4 * OC),
           x.data_ptr(), w.data_ptr(), b.data_ptr(), main.data_ptr(), _ptr(conf), NB, H, W,
-                                   OC, mode, _dt(x), _stream())
+                                   OC, mode, _dt(x), _STREAM)
     return main, conf
 
 
@@ -235,17 +250,17 @@ def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    _call("iggt_skinny_gemm", 2.0 * M * N * K, 2.0 * N * K + 4.0 * M * (K + N),
+    _call(x, "iggt_skinny_gemm", 2.0 * M * N * K, 2.0 * N * K + 4.0 * M * (K + N),
           x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(gamma),
                                       _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(),
-                                      out.stride(0), M, N, K, act, _dt(w), _stream())
+                                      out.stride(0), M, N, K, act, _dt(w), _STREAM)
     return out
 
 
 def small_attention(qkv, B, N, H, d):
     out = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
-    _call("iggt_small_attention", 4.0 * B * N * N * H * d, 16.0 * B * N * H * d,
-          qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _stream())
+    _call(qkv, "iggt_small_attention", 4.0 * B * N * N * H * d, 16.0 * B * N * H * d,
+          qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _STREAM)
     return out
 
 
@@ -256,15 +271,15 @@ def layernorm16(x, w, b, eps=1e-5, out=None):
     rows = x.numel() // C
     if out is None:
         out = torch.empty_like(x)
-    _call("iggt_layernorm16", 0, 4.0 * x.numel(), x.data_ptr(), out.data_ptr(), rows, C, w.data_ptr(), b.data_ptr(),
-          float(eps), _dt(x), _stream())
+    _call(x, "iggt_layernorm16", 0, 4.0 * x.numel(), x.data_ptr(), out.data_ptr(), rows, C, w.data_ptr(), b.data_ptr(),
+          float(eps), _dt(x), _STREAM)
     return out
 
 
 def col2im_k4s2p1(y, bias, NB, h, w, C):
     out = torch.empty((NB, 2 * h, 2 * w, C), dtype=y.dtype, device=y.device)
-    _call("iggt_col2im_k4s2p1", 0, 2.0 * (y.numel() + out.numel()), y.data_ptr(), bias.data_ptr(), out.data_ptr(),
-          NB, h, w, C, _dt(y), _stream())
+    _call(y, "iggt_col2im_k4s2p1", 0, 2.0 * (y.numel() + out.numel()), y.data_ptr(), bias.data_ptr(), out.data_ptr(),
+          NB, h, w, C, _dt(y), _STREAM)
     return out
 
 
@@ -273,9 +288,9 @@ def ocab_attention(q, k, v, table, rpi):
     NB, h, w, C = q.shape
     assert C == 256 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     out = torch.empty_like(q)
-    _call("iggt_ocab_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 144 * 64, 8.0 * q.numel(),
+    _call(q, "iggt_ocab_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 144 * 64, 8.0 * q.numel(),
           q.data_ptr(), k.data_ptr(), v.data_ptr(), table.data_ptr(), rpi.data_ptr(), out.data_ptr(), NB, h, w,
-          _dt(q), _stream())
+          _dt(q), _STREAM)
     return out
 
 
@@ -284,8 +299,8 @@ def window_attention(qkv):
     NB, h, w, C3 = qkv.shape
     assert C3 == 384 and qkv.is_contiguous()
     out = torch.empty((NB, h, w, 128), dtype=qkv.dtype, device=qkv.device)
-    _call("iggt_window_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 64 * 32, 2.0 * (qkv.numel() + out.numel()),
-          qkv.data_ptr(), out.data_ptr(), NB, h, w, _dt(qkv), _stream())
+    _call(qkv, "iggt_window_attention", 4.0 * NB * (h // 8) * (w // 8) * 4 * 64 * 64 * 32, 2.0 * (qkv.numel() + out.numel()),
+          qkv.data_ptr(), out.data_ptr(), NB, h, w, _dt(qkv), _STREAM)
     return out
 
 
@@ -293,16 +308,16 @@ def channel_mean(x):
     """x [NB,h,w,C] 16-bit -> [NB,C] fp32 spatial means."""
     NB, h, w, C = x.shape
     mean = torch.empty((NB, C), dtype=torch.float32, device=x.device)
-    _call("iggt_channel_mean", 0, 2.0 * x.numel(), x.data_ptr(), mean.data_ptr(), NB, h * w, C, _dt(x), _stream())
+    _call(x, "iggt_channel_mean", 0, 2.0 * x.numel(), x.data_ptr(), mean.data_ptr(), NB, h * w, C, _dt(x), _STREAM)
     return mean
 
 
 def se_scale_add(y0, cx, mean, w1, b1, w2, b2, alpha):
     NB, h, w, C = y0.shape
     out = torch.empty_like(y0)
-    _call("iggt_se_scale_add", 0, 6.0 * y0.numel(), y0.data_ptr(), cx.data_ptr(), mean.data_ptr(), w1.data_ptr(),
+    _call(y0, "iggt_se_scale_add", 0, 6.0 * y0.numel(), y0.data_ptr(), cx.data_ptr(), mean.data_ptr(), w1.data_ptr(),
           b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), NB, h * w, C, w1.shape[0], float(alpha),
-          _dt(y0), _stream())
+          _dt(y0), _STREAM)
     return out
 
 
@@ -313,7 +328,7 @@ def pose_to_cameras(pose_enc, H, W, build_intrinsics=True):
     n = p.numel() // 9
     extr = torch.empty(p.shape[:-1] + (3, 4), dtype=torch.float32, device=p.device)
     intr = torch.empty(p.shape[:-1] + (3, 3), dtype=torch.float32, device=p.device) if build_intrinsics else None
-    _call("iggt_pose_to_cameras", 0, 30.0 * 4 * n, p.data_ptr(), extr.data_ptr(), _ptr(intr), n, H, W, _stream())
+    _call(pose_enc, "iggt_pose_to_cameras", 0, 30.0 * 4 * n, p.data_ptr(), extr.data_ptr(), _ptr(intr), n, H, W, _STREAM)
     return extr, intr
 
 
@@ -327,8 +342,8 @@ def unproject_depth(depth, extrinsics, intrinsics, eps=1e-8, z_far=100.0, with_m
     k = intrinsics.reshape(n, 3, 3).contiguous()
     world = torch.empty((n, H, W, 3), dtype=torch.float32, device=d.device)
     mask = torch.empty((n, H, W), dtype=torch.uint8, device=d.device) if with_mask else None
-    _call("iggt_unproject_depth", 0, 17.0 * d.numel(), d.data_ptr(), e.data_ptr(), k.data_ptr(), world.data_ptr(),
-          _ptr(mask), n, H, W, float(eps), float(z_far), _stream())
+    _call(depth, "iggt_unproject_depth", 0, 17.0 * d.numel(), d.data_ptr(), e.data_ptr(), k.data_ptr(), world.data_ptr(),
+          _ptr(mask), n, H, W, float(eps), float(z_far), _STREAM)
     return world, (mask.bool() if mask is not None else None)
 
 
@@ -349,10 +364,10 @@ def resample_bicubic_u8(src, kk_h, bounds_h, kk_v, bounds_v, out, oy0=0):
     last = int(bv[-1, 0] + bv[-1, 1])
     assert 0 <= first < last <= h_in
     tmp = torch.empty((last - first, w_out, 3), dtype=torch.uint8, device=src.device)
-    _call("iggt_resample_h_u8", 0, float((last - first) * 3 * (w_in + w_out)), src[first:].data_ptr(), w_in * 3,
-          last - first, w_out, kk_h.data_ptr(), bounds_h.data_ptr(), kk_h.shape[1], tmp.data_ptr(), _stream())
-    _call("iggt_resample_v_u8_f32", 0, float(tmp.numel() + out.numel() * 4), tmp.data_ptr(), w_out, kk_v.data_ptr(),
-          bounds_v.data_ptr(), kk_v.shape[1], first, oy0, rows, out.data_ptr(), out.stride(0), out.stride(1), _stream())
+    _call(src, "iggt_resample_h_u8", 0, float((last - first) * 3 * (w_in + w_out)), src[first:].data_ptr(), w_in * 3,
+          last - first, w_out, kk_h.data_ptr(), bounds_h.data_ptr(), kk_h.shape[1], tmp.data_ptr(), _STREAM)
+    _call(src, "iggt_resample_v_u8_f32", 0, float(tmp.numel() + out.numel() * 4), tmp.data_ptr(), w_out, kk_v.data_ptr(),
+          bounds_v.data_ptr(), kk_v.shape[1], first, oy0, rows, out.data_ptr(), out.stride(0), out.stride(1), _STREAM)
     return out
 
 
@@ -367,13 +382,13 @@ def knn_mean_features(points, feats, k, return_graph=False, stats=None):
     dev = pts.device
     lo, hi = pts.amin(0).contiguous(), pts.amax(0).contiguous()
     codes = torch.empty(n, dtype=torch.int64, device=dev)
-    _call("iggt_knn_morton", 0, 20.0 * n, pts.data_ptr(), n, lo.data_ptr(), hi.data_ptr(), codes.data_ptr(), _stream())
+    _call(points, "iggt_knn_morton", 0, 20.0 * n, pts.data_ptr(), n, lo.data_ptr(), hi.data_ptr(), codes.data_ptr(), _STREAM)
     order = torch.argsort(codes)
     nblocks = (n + 255) // 256
     sorted4 = torch.empty((n, 4), dtype=torch.float32, device=dev)
     aabb = torch.empty((nblocks, 6), dtype=torch.float32, device=dev)
-    _call("iggt_knn_reorder", 0, 36.0 * n, pts.data_ptr(), order.data_ptr(), n, sorted4.data_ptr(), aabb.data_ptr(),
-          _stream())
+    _call(points, "iggt_knn_reorder", 0, 36.0 * n, pts.data_ptr(), order.data_ptr(), n, sorted4.data_ptr(), aabb.data_ptr(),
+          _STREAM)
     out = None
     F = 0
     if feats is not None:
@@ -383,8 +398,8 @@ def knn_mean_features(points, feats, k, return_graph=False, stats=None):
         out = torch.empty_like(feats)
     idx = torch.empty((n, k), dtype=torch.int32, device=dev) if return_graph else None
     d2 = torch.empty((n, k), dtype=torch.float32, device=dev) if return_graph else None
-    _call("iggt_knn_mean_features", 0, float(n) * (16 + 4 * F * (k + 1)), sorted4.data_ptr(), aabb.data_ptr(), n, k,
-          _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _ptr(stats), _stream())
+    _call(points, "iggt_knn_mean_features", 0, float(n) * (16 + 4 * F * (k + 1)), sorted4.data_ptr(), aabb.data_ptr(), n, k,
+          _ptr(feats), F, _ptr(out), _ptr(idx), _ptr(d2), _ptr(stats), _STREAM)
     return (out, idx, d2) if return_graph else out
 
 
@@ -395,7 +410,7 @@ def avgpool2_nhwc(x):
     assert x.is_cuda and x.is_contiguous() and x.dim() == 4
     NB, H, W, C = x.shape
     y = torch.empty((NB, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
-    _call("iggt_avgpool2_nhwc", 0, 2.0 * (x.numel() + y.numel()), x.data_ptr(), y.data_ptr(), NB, H, W, C, _dt(x), _stream())
+    _call(x, "iggt_avgpool2_nhwc", 0, 2.0 * (x.numel() + y.numel()), x.data_ptr(), y.data_ptr(), NB, H, W, C, _dt(x), _STREAM)
     return y
 
 
@@ -406,8 +421,8 @@ def sample_bilinear_nhwc(x, coords):
     coords = coords.contiguous()
     R = coords.shape[1]
     out = torch.empty((NB, R, C), dtype=torch.float32, device=x.device)
-    _call("iggt_sample_bilinear_nhwc", 0, 12.0 * out.numel(), x.data_ptr(), coords.data_ptr(), out.data_ptr(), NB, R, H, W,
-          C, _dt(x), _stream())
+    _call(x, "iggt_sample_bilinear_nhwc", 0, 12.0 * out.numel(), x.data_ptr(), coords.data_ptr(), out.data_ptr(), NB, R, H, W,
+          C, _dt(x), _STREAM)
     return out
 
 
@@ -423,9 +438,9 @@ def corr_sample(levels, targets, coords, B, N, S, ldo=576):
     ptrs = (ctypes.c_void_p * 7)(*[l.data_ptr() for l in levels])
     Hs = (ctypes.c_int * 7)(*[l.shape[1] for l in levels])
     Ws = (ctypes.c_int * 7)(*[l.shape[2] for l in levels])
-    _call("iggt_corr_sample", 2.0 * rows * 7 * 100 * 128, rows * 7.0 * 100 * 256,
+    _call(targets, "iggt_corr_sample", 2.0 * rows * 7 * 100 * 128, rows * 7.0 * 100 * 256,
           ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(Hs, ctypes.c_void_p), ctypes.cast(Ws, ctypes.c_void_p),
-          targets.data_ptr(), coords.data_ptr(), out.data_ptr(), B, N, S, ldo, _dt(levels[0]), _stream())
+          targets.data_ptr(), coords.data_ptr(), out.data_ptr(), B, N, S, ldo, _dt(levels[0]), _STREAM)
     return out
 
 
@@ -437,9 +452,9 @@ def track_input(coords, fcorr, tfeat, pos, ref_tok, ln_w, ln_b, S, dtype, ldo=39
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
     out = torch.empty((rows, ldo), dtype=dtype, device=coords.device)
     raw = torch.empty((rows, 388), dtype=torch.float32, device=coords.device) if want_raw else None
-    _call("iggt_track_input", 0, rows * (388.0 * 6 + 2 * ldo), coords.data_ptr(), fcorr.data_ptr(), tfeat.data_ptr(),
+    _call(coords, "iggt_track_input", 0, rows * (388.0 * 6 + 2 * ldo), coords.data_ptr(), fcorr.data_ptr(), tfeat.data_ptr(),
           pos.data_ptr(), ref_tok.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), out.data_ptr(), _ptr(raw), rows, S, ldo,
-          1e-5, F16 if dtype == torch.float16 else BF16, _stream())
+          1e-5, F16 if dtype == torch.float16 else BF16, _STREAM)
     return (out, raw) if want_raw else out
 
 
@@ -454,6 +469,6 @@ def layernorm_rows(x, w, b, eps=1e-5, out32=None, out16=None):
     if out16 is not None:
         assert out16.is_contiguous() and out16.shape[0] == rows and out16.shape[1] >= C
         ld16, dt = out16.shape[1], _dt(out16)
-    _call("iggt_layernorm_rows", 0, rows * C * 10.0, x.data_ptr(), x.stride(0), C, w.data_ptr(), b.data_ptr(), float(eps),
-          rows, _ptr(out32), _ptr(out16), ld16, dt, _stream())
+    _call(x, "iggt_layernorm_rows", 0, rows * C * 10.0, x.data_ptr(), x.stride(0), C, w.data_ptr(), b.data_ptr(), float(eps),
+          rows, _ptr(out32), _ptr(out16), ld16, dt, _STREAM)
     return out32, out16

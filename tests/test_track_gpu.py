@@ -50,12 +50,6 @@ def test_sample_bilinear_border(ops, dtype):
     assert got.dtype == torch.float32 and _rel(got, emu_ops.sample_bilinear_nhwc(x, coords)) < 1e-5
 
 
-PENDING = ("first GPU run (round 1): 29 / 31 of this file passed; the correlation lookup did not reproduce the reference's "
-           "degenerate 1 x 1 pyramid level.  The fix (csrc/track.cu, flat_x / flat_y) was committed after the round's "
-           "GPU budget was spent, so these two are expected-to-pass-but-unverified: non-strict xfail until re-run.")
-
-
-@pytest.mark.xfail(reason=PENDING, strict=False)
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_corr_sample(ops, dtype):
     g = torch.Generator().manual_seed(2)
@@ -125,9 +119,7 @@ def test_attention_update_transformer_shapes(ops, dtype, num_seq, Lq, Lk):
     assert _rel(got, want) < 2 * _tol(dtype)
 
 
-@pytest.mark.xfail(reason=PENDING, strict=False)
-def test_forward_with_query_points_teacher_forced(monkeypatch):
-    monkeypatch.setenv("IGGT_TRACK_HEAD", "1")
+def test_forward_with_query_points_teacher_forced():
     from oracle import ref_model, ref_track, weights
     from iggt_official_b200.models.vggt import VGGT
     rec = torch.load(FIX)
@@ -169,3 +161,36 @@ def test_forward_with_query_points_teacher_forced(monkeypatch):
         assert _rel(trace[i]["delta"], rec["delta"][i]) < 6e-2, (i, _rel(trace[i]["delta"], rec["delta"][i]))
         assert (preds[i].cpu() - rec["track_all_iters"][i]).abs().max().item() < 0.5   # pixels
     assert (vis.cpu() - rec["vis"]).abs().max().item() < 5e-2 and (conf.cpu() - rec["conf"]).abs().max().item() < 5e-2
+
+
+def test_free_running_first_iteration_and_13_views():
+    """(a) One free-running refinement iteration (no teacher forcing: the module's own feature maps, correlation lookup
+    and state) against the oracle's tracker run on the SAME 16-bit feature maps - the first iteration is before the
+    loop turns chaotic, so it is compared directly.  (b) S = 13 views with query points: the reference's frame-chunk
+    path raises for S > 12; here it must simply work, and frame 0 stays pinned to the query points."""
+    from oracle import ref_track, weights
+    from iggt_official_b200.models.vggt import VGGT
+    rec = torch.load(FIX)
+    c = rec["case"]
+    sd = weights.make_state_dict(c["wseed"], c["kind"])
+    m = VGGT()
+    m.load_state_dict(sd, strict=False)
+    m.eval().to("cuda")
+    m.compute_dtype = torch.float16
+    g = torch.Generator().manual_seed(c["iseed"])
+    images = torch.rand(c["S"], 3, c["H"], c["W"], generator=g).cuda()
+    qp = rec["query_points"]
+    tokens, psi = m.aggregator(images[None], compute_dtype=torch.float16)
+    fm = m.track_head.feature_extractor(tokens, images[None], psi, compute_dtype=torch.float16)
+    preds, vis, conf = m.track_head.track(fm, qp[None].cuda(), 1, c["S"], 1, torch.float16)
+    sdt = {k: v for k, v in sd.items() if k.startswith("track_head.")}
+    fm_nchw = fm.float().permute(0, 3, 1, 2).view(1, c["S"], 128, *fm.shape[1:3]).cpu()
+    want, wvis, wconf = ref_track.tracker(sdt, qp[None].float(), fm_nchw, iters=1)
+    assert (preds[0].cpu() - want[0]).abs().max().item() < 0.5                     # pixels, after one update
+    assert (vis.cpu() - wvis).abs().max().item() < 5e-2 and (conf.cpu() - wconf).abs().max().item() < 5e-2
+    g13 = torch.Generator().manual_seed(3)
+    imgs13 = torch.rand(13, 3, 140, 154, generator=g13).cuda()
+    out = m(imgs13, query_points=qp.cuda())
+    assert out["track"].shape == (1, 13, c["N"], 2) and out["vis"].shape == (1, 13, c["N"]) == out["conf"].shape
+    assert torch.equal(out["track"][:, 0].cpu(), qp[None]) and torch.isfinite(out["track"]).all()
+    assert torch.isfinite(out["vis"]).all() and torch.isfinite(out["conf"]).all()

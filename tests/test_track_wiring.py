@@ -59,12 +59,12 @@ def test_track_module_wiring_teacher_forced(monkeypatch):
     assert (vis - rec["vis"]).abs().max().item() < 1e-4 and (conf - rec["conf"]).abs().max().item() < 1e-4
 
 
-def test_query_points_are_opt_in(monkeypatch):
-    """Until the correlation lookup has been re-verified on a GPU the track branch needs IGGT_TRACK_HEAD=1."""
+def test_query_points_run_by_default():
+    """The track branch is on by default (reference: iggt/models/vggt.py:220-226): with CPU tensors the call reaches
+    the CUDA-only guard of the hot path instead of a NotImplementedError / an opt-in switch."""
     import pytest
     from iggt_official_b200.models.vggt import VGGT
-    monkeypatch.delenv("IGGT_TRACK_HEAD", raising=False)
-    with pytest.raises(NotImplementedError, match="IGGT_TRACK_HEAD=1"):
+    with pytest.raises(RuntimeError, match="CUDA"):
         VGGT()(torch.zeros(2, 3, 28, 28), query_points=torch.zeros(3, 2))
 
 
