@@ -15,6 +15,7 @@ All activations are NHWC 16-bit; every convolution runs on the tcgen05 implicit-
 The reference runs these heads in fp32 / TF32 (iggt/models/vggt.py:189); 16-bit operands with fp32 accumulate
 have the same 10-bit mantissa as TF32 when the compute dtype is fp16.
 """
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -24,6 +25,7 @@ from ..layout import Node
 
 PATCH = 14
 LAYERS = (4, 11, 17, 23)
+FUSED_TAIL = os.environ.get("IGGT_FUSED_TAIL", "1") != "0"
 
 
 def uv_pos_tables(gh: int, gw: int, ch: int, aspect: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -55,6 +57,16 @@ def pack_deconv(w, b, dtype, device):
     k = w.shape[2]
     wp = w.detach().to(device).permute(2, 3, 1, 0).reshape(k * k * w.shape[1], w.shape[0]).to(dtype).contiguous()
     return wp, b.detach().to(device, torch.float32).repeat(k * k).contiguous()
+
+
+def dense_tail(up, pk, mode):
+    """`output_conv2` + head activation on the full-resolution 128-channel map: one launch of the tall-box kernel
+    (csrc/tailconv.cu; the 32-channel map stays in fp32 registers).  IGGT_FUSED_TAIL=0 selects the two-launch form
+    (generic implicit-GEMM conv -> 16-bit map -> per-pixel tail) for A/B checks."""
+    if FUSED_TAIL and up.shape[3] == 128 and pk["oc2a.w"].shape[0] == 32:
+        return ops.dpt_tail_fused(up, pk["oc2a.w"], pk["oc2a.b"], pk["oc2b.w"], pk["oc2b.b"], mode)
+    z = ops.conv_nhwc(up, pk["oc2a.w"], pk["oc2a.b"], act=2)
+    return ops.dpt_tail(z, pk["oc2b.w"], pk["oc2b.b"], mode)
 
 
 def _f32(p, device):
@@ -216,8 +228,7 @@ class DPTHead(Node):
             feats = self._pyramid(pk, aggregated_tokens_list, NI, n0, n1, gh, gw, T, aspect, dt, dev)
             o, (o2, o3, o4) = self._scratch(pk, feats)
             up = ops.upsample_bilinear(o, gh * PATCH, gw * PATCH, tx, ty)
-            z = ops.conv_nhwc(up, pk["oc2a.w"], pk["oc2a.b"], act=2)
-            m, c = ops.dpt_tail(z, pk["oc2b.w"], pk["oc2b.b"], mode)
+            m, c = dense_tail(up, pk, mode)
             preds[n0:n1].copy_(m)
             conf[n0:n1].copy_(c)
             if self.use_point_feat:

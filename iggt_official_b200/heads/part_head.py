@@ -18,7 +18,7 @@ import torch
 
 from .. import ops
 from ..layout import Node
-from .dpt_head import DPTHead, LAYERS, PATCH, _f32, pack_conv3x3, pack_deconv
+from .dpt_head import DPTHead, LAYERS, PATCH, _f32, dense_tail, pack_conv3x3, pack_deconv
 
 
 def _h16(p, dtype, device):
@@ -304,7 +304,6 @@ class PartHead(DPTHead):
             f = ops.conv_nhwc(o1, pk["oc1.w"], pk["oc1.b"])                                  # [nb, 8g, 8g, 128]
             f = self._swin_sa(pk, f)
             up = ops.upsample_bilinear(f, gh * PATCH, gw * PATCH)
-            z = ops.conv_nhwc(up, pk["oc2a.w"], pk["oc2a.b"], act=2)
-            m, _ = ops.dpt_tail(z, pk["oc2b.w"], pk["oc2b.b"], 2)
+            m, _ = dense_tail(up, pk, 2)
             out[n0:n1].copy_(m)
         return out.view(B, S, 8, H, W)

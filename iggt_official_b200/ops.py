@@ -242,6 +242,35 @@ def dpt_tail(x, w, b, mode):
     return main, conf
 
 
+def dpt_tail_fused(x, wp, bias, w2, b2, mode):
+    """x [NB,H,W,128] 16-bit NHWC -> 3x3 conv (wp [32, 9*128] tap-major) + bias + ReLU -> 1x1 (w2 [OC,32] fp32) ->
+    head activation, one launch (csrc/tailconv.cu).  Returns (main, conf) like `dpt_tail`."""
+    assert x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.shape[3] == 128
+    assert wp.shape == (32, 9 * 128) and wp.is_contiguous() and wp.dtype == x.dtype
+    NB, H, W, _ = x.shape
+    OC = w2.shape[0]
+    if mode == 2:
+        main = torch.empty((NB, OC, H, W), dtype=torch.float32, device=x.device)
+        conf = None
+    else:
+        main = torch.empty((NB, H, W, OC - 1), dtype=torch.float32, device=x.device)
+        conf = torch.empty((NB, H, W), dtype=torch.float32, device=x.device)
+    _call(x, "iggt_dpt_tail_fused", 2.0 * NB * H * W * 32 * (9 * 128 + OC), NB * H * W * (256.0 + 4 * OC),
+          x.data_ptr(), wp.data_ptr(), bias.data_ptr(), w2.data_ptr(), b2.data_ptr(), main.data_ptr(), _ptr(conf), 0,
+          NB, H, W, OC, mode, _dt(x), _STREAM)
+    return main, conf
+
+
+def conv3x3_c128_relu(x, wp, bias):
+    """The unfused form of `dpt_tail_fused` (same kernel, stores the 32-channel ReLU map): for A/B checks."""
+    assert x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.shape[3] == 128 and wp.shape == (32, 9 * 128)
+    NB, H, W, _ = x.shape
+    out = torch.empty((NB, H, W, 32), dtype=x.dtype, device=x.device)
+    _call(x, "iggt_dpt_tail_fused", 2.0 * NB * H * W * 32 * 9 * 128, NB * H * W * (256.0 + 64),
+          x.data_ptr(), wp.data_ptr(), bias.data_ptr(), 0, 0, 0, 0, out.data_ptr(), NB, H, W, 0, 0, _dt(x), _STREAM)
+    return out
+
+
 def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
     """fp32 x [M<=32, K] times 16-bit w [N, K]^T -> fp32 [M, N]."""
     _chk2d(x); _chk2d(w)

@@ -251,6 +251,13 @@ def dpt_tail(x, w, b, mode):
     return main.contiguous(), (1 + o[..., -1].exp()).contiguous()
 
 
+def dpt_tail_fused(x, wp, bias, w2, b2, mode):
+    """conv3x3(128 -> 32) + bias + ReLU kept in fp32 (no 16-bit rounding of the 32-channel map), then `dpt_tail`."""
+    w = wp.float().view(32, 3, 3, 128).permute(0, 3, 1, 2)
+    z = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=1)).permute(0, 2, 3, 1)
+    return dpt_tail(z, w2, b2, mode)
+
+
 def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
     v = x @ w.float().t()
     if bias is not None:
