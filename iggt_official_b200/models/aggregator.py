@@ -37,18 +37,21 @@ def pack_block(blk, dtype, device, qk_norm) -> _BlockW:
     w = _BlockW()
     f32 = lambda p: p.detach().to(device=device, dtype=torch.float32).contiguous()
     h16 = lambda p: p.detach().to(device=device, dtype=dtype).contiguous()
+    # autocast casts a Linear's bias to the 16-bit dtype like its other operands (pinned against real autocast by
+    # tests/test_oracle_amp.py); the epilogues add it in fp32, so it is rounded once here
+    b16 = lambda p: p.detach().to(device=device, dtype=dtype).to(torch.float32).contiguous()
     w.n1w, w.n1b = f32(blk.norm1.weight), f32(blk.norm1.bias)
-    w.qkv_w, w.qkv_b = h16(blk.attn.qkv.weight), f32(blk.attn.qkv.bias)
+    w.qkv_w, w.qkv_b = h16(blk.attn.qkv.weight), b16(blk.attn.qkv.bias)
     if qk_norm:
         w.qn_w, w.qn_b = f32(blk.attn.q_norm.weight), f32(blk.attn.q_norm.bias)
         w.kn_w, w.kn_b = f32(blk.attn.k_norm.weight), f32(blk.attn.k_norm.bias)
     else:
         w.qn_w = w.qn_b = w.kn_w = w.kn_b = None
-    w.proj_w, w.proj_b = h16(blk.attn.proj.weight), f32(blk.attn.proj.bias)
+    w.proj_w, w.proj_b = h16(blk.attn.proj.weight), b16(blk.attn.proj.bias)
     w.ls1 = f32(blk.ls1.gamma)
     w.n2w, w.n2b = f32(blk.norm2.weight), f32(blk.norm2.bias)
-    w.fc1_w, w.fc1_b = h16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
-    w.fc2_w, w.fc2_b = h16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+    w.fc1_w, w.fc1_b = h16(blk.mlp.fc1.weight), b16(blk.mlp.fc1.bias)
+    w.fc2_w, w.fc2_b = h16(blk.mlp.fc2.weight), b16(blk.mlp.fc2.bias)
     w.ls2 = f32(blk.ls2.gamma)
     return w
 
@@ -102,7 +105,7 @@ class Aggregator(Node):
         wp = torch.zeros(1024, KP, device=device, dtype=dtype)
         wp[:, :588] = w.to(dtype)
         pk["pe_w"] = wp
-        pk["pe_b"] = pe.patch_embed.proj.bias.detach().to(device, torch.float32).contiguous()
+        pk["pe_b"] = pe.patch_embed.proj.bias.detach().to(device, dtype).to(torch.float32).contiguous()   # as above
         pk["cls"] = pe.cls_token.detach().to(device, torch.float32).reshape(-1).contiguous()
         pk["reg"] = pe.register_tokens.detach().to(device, torch.float32).reshape(NUM_REG, -1).contiguous()
         pk["dino_norm_w"] = pe.norm.weight.detach().to(device, torch.float32).contiguous()

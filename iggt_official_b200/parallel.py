@@ -59,18 +59,18 @@ def forward_sharded(model, images_local: torch.Tensor, rank: int, world: int, gr
     if images_local.dim() == 4:
         images_local = images_local.unsqueeze(0)
     B, S_loc = images_local.shape[:2]
-    dt = model._dtype()
+    dt, hd = model._dtype(), model._head_dtype()
     tokens, psi = model.aggregator(images_local, compute_dtype=dt, view_offset=rank * S_loc,
                                    total_views=world * S_loc)
     cam = gather_camera_tokens(tokens[23], group, world)
-    pred = {"pose_enc": model.camera_head(tokens, compute_dtype=dt, camera_tokens=cam)}
-    d, dc = model.depth_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
-    out = model.point_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
+    pred = {"pose_enc": model.camera_head(tokens, compute_dtype=hd, camera_tokens=cam)}
+    d, dc = model.depth_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=hd)
+    out = model.point_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=hd)
     pred["depth"], pred["depth_conf"] = d, dc
     pred["world_points"], pred["world_points_conf"] = out[0], out[1]
     if getattr(model, "_with_part", False) and getattr(model, "part_enabled", True):
-        maps = model.part_adaptor(tokens, images=images_local, patch_start_idx=psi, compute_dtype=dt)
+        maps = model.part_adaptor(tokens, images=images_local, patch_start_idx=psi, compute_dtype=hd)
         pred["part_feat"] = model.part_head(maps, point_feature=out[2], images=images_local, patch_start_idx=psi,
-                                            compute_dtype=dt)
+                                            compute_dtype=hd)
     pred["images"] = images_local
-    return pred
+    return model._check(pred)

@@ -23,6 +23,15 @@ RESNET_STD = (0.229, 0.224, 0.225)
 
 
 # ----------------------------------------------------------------------------- precision helpers
+# Which autocast the `amp` mode restates.  "cuda" (default) is what demo.py runs: layer_norm is on CUDA autocast's
+# fp32 list, so q_norm / k_norm and the RoPE that follows run in fp32.  "cpu" restates torch.autocast("cpu", ...),
+# whose policy has no fp32 entry for layer_norm: q_norm / k_norm outputs, the RoPE tables (rope.py:100-116, cached in
+# the tokens' dtype) and every RoPE product / sum are 16-bit.  The "cpu" variant exists only so that the 16-bit
+# rounding points of this restatement can be pinned against the UNMODIFIED reference run under CPU autocast in this
+# container (oracle/make_golden_amp.py, tests/test_oracle_amp.py); parity tests of the CUDA path use "cuda".
+AUTOCAST_DEVICE = "cuda"
+
+
 def _r(x, amp):
     """round to the autocast dtype and come back to fp32 (fp32 accumulate, 16-bit storage)"""
     return x if amp is None else x.to(amp).float()
@@ -54,9 +63,16 @@ def rope_tables(npos, device):
     return ang.cos(), ang.sin()
 
 
-def rope_2d(t, pos):
-    """t [b, heads, n, 64], pos [b, n, 2] (y, x) int64 -- rope.py:119-131,154-188."""
-    cos16, sin16 = rope_tables(int(pos.max()) + 1, t.device)
+def rope_2d(t, pos, amp=None):
+    """t [b, heads, n, 64], pos [b, n, 2] (y, x) int64 -- rope.py:119-131,154-188.  `amp` is only passed under the
+    "cpu" autocast policy (16-bit tokens: the tables are built from 16-bit angles and every product / sum is rounded)."""
+    if amp is None:
+        cos16, sin16 = rope_tables(int(pos.max()) + 1, t.device)
+    else:                                                   # rope.py:110-114 with dtype = the 16-bit token dtype
+        exponents = torch.arange(0, 32, 2, device=t.device).float() / 32
+        ang = torch.einsum("i,j->ij", torch.arange(int(pos.max()) + 1, device=t.device, dtype=torch.float32),
+                           1.0 / (100.0 ** exponents)).to(amp)
+        cos16, sin16 = ang.cos().float(), ang.sin().float()
     cos = torch.cat([cos16, cos16], -1)
     sin = torch.cat([sin16, sin16], -1)
 
@@ -65,7 +81,7 @@ def rope_2d(t, pos):
 
     def one(x, p):
         c, s = cos[p][:, None], sin[p][:, None]
-        return x * c + rot(x) * s
+        return _r(_r(x * c, amp) + _r(rot(x) * s, amp), amp)
 
     return torch.cat([one(t[..., :32], pos[..., 0]), one(t[..., 32:], pos[..., 1])], -1)
 
@@ -88,8 +104,11 @@ def attention(sd, pre, x, heads, qk_norm, pos, amp):
     if qk_norm:
         q = F.layer_norm(q, (d,), sd[pre + "q_norm.weight"], sd[pre + "q_norm.bias"], 1e-5)
         k = F.layer_norm(k, (d,), sd[pre + "k_norm.weight"], sd[pre + "k_norm.bias"], 1e-5)
+    cpu_policy = amp if (amp is not None and AUTOCAST_DEVICE == "cpu") else None
+    if qk_norm:
+        q, k = _r(q, cpu_policy), _r(k, cpu_policy)
     if pos is not None:
-        q, k = rope_2d(q, pos), rope_2d(k, pos)
+        q, k = rope_2d(q, pos, cpu_policy), rope_2d(k, pos, cpu_policy)
     o = sdpa(q, k, v, d ** -0.5, amp)
     o = o.transpose(1, 2).reshape(b, n, c)
     return linear(o, sd[pre + "proj.weight"], sd[pre + "proj.bias"], amp)

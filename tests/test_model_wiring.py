@@ -43,7 +43,7 @@ def test_model_graph_with_emulated_launchers_matches_reference_fixture(monkeypat
     m = (IGGT if c["model"] == "IGGT" else VGGT)()
     m.load_state_dict(weights.make_state_dict(c["wseed"], c["kind"]), strict=False)
     m.eval()
-    m.compute_dtype = torch.float32                                          # "16-bit" operands kept exact
+    m.compute_dtype = m.head_dtype = torch.float32                           # "16-bit" operands kept exact
     g = torch.Generator().manual_seed(c["iseed"])
     images = torch.rand(c["B"], c["S"], 3, c["H"], c["W"], generator=g)
     out = m(images[0] if c["B"] == 1 else images)

@@ -67,7 +67,7 @@ def _sharded_worker(rank, world, port, ret):
     agg_mod._require_cuda = lambda images: None
     torch.manual_seed(0)                                   # identical random-init weights on every rank
     m = VGGT().eval()
-    m.compute_dtype = torch.float32
+    m.compute_dtype = m.head_dtype = torch.float32
     g = torch.Generator().manual_seed(3)
     B, S, H, W = 2, 4, 28, 42
     images = torch.rand(B, S, 3, H, W, generator=g)
