@@ -8,13 +8,16 @@ reference architecture, fp16 trunk operands (fp32 accumulate / residual / LayerN
 reference can produce at this (odd, 37x37) patch grid: pose_enc, depth(+conf), world_points(+conf).
 `part_feat` needs an even patch grid in the reference and is reported by `--size 532`.
 
-N>1 (launched by torchrun, one rank per GPU): the 8 views are sharded over the ranks (strong scaling) with
-one NCCL all-gather of K|V per global block.
+N>1 (launched by torchrun, one rank per GPU): the views of every scene are sharded over the ranks (strong scaling)
+with one all-gather of K|V per global block.  `--scenes B --views S` select the other BASELINE configs:
+C3 = `--views 32` on 8 GPUs (4 views per GPU), C5 = `--scenes 4 --views 16 --dtype bf16` on 8 GPUs (each GPU holds
+2 views of all 4 scenes), C4 = `--size 1036 --part`.
 
 A step = one forward over the batch.  `value` is timed with inputs resident in HBM; `e2e` includes the
 pinned-host -> device copy of the images and the device -> host copy of every prediction, each step.
-`--impl reference` times the reference algorithm's CPU implementation (the oracle port, all host threads)
-on a bounded sample of the same workload (2 views at the same resolution).
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port, all host threads) on a
+bounded sample of the same workload: `--ref-views` (default 1) of the views per step at the same resolution - its
+`config` says so (`views_per_step`), its global attention spans that many views only.
 """
 import argparse
 import json
@@ -128,16 +131,24 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "views/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": dict(workload_config(args, 1), views_per_step=S, sample=sample,
+                           parallelism=f"host CPU, {cores} threads"),
             "cpu_baseline": {"value": v, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+def config_name(args):
+    key = (args.scenes, args.views, args.size)
+    return {(1, 8, 518): "C2", (1, 32, 518): "C3", (1, 8, 1036): "C4", (4, 16, 518): "C5"}.get(key, "custom")
+
+
 def workload_config(args, world):
-    return {"workload": f"C2: 1 scene x {args.views} views, {args.size}x{args.size}, full forward "
+    return {"workload": f"{config_name(args)}: {args.scenes} scene{'s' if args.scenes > 1 else ''} x {args.views} views, "
+                        f"{args.size}x{args.size}, full forward "
                         f"(pose_enc, depth+conf, world_points+conf{', part_feat' if args.part else ''})",
-            "views": args.views, "image": [args.size, args.size], "weights": "random-init, reference architecture (1.30 B params)",
+            "scenes": args.scenes, "views": args.views, "image": [args.size, args.size],
+            "weights": "random-init, reference architecture (1.30 B params)",
             "parallelism": f"view-shard x{world}" if world > 1 else "single GPU",
             "l2": "per-step working set (2.6 GB 16-bit weights + activations) >> 126 MB L2: no flush needed"}
 
@@ -158,7 +169,7 @@ def run_b200(args):
     assert args.views % world == 0, "views must divide over the ranks"
     S_loc = args.views // world
     g = torch.Generator().manual_seed(0)
-    images_host = torch.rand(1, args.views, 3, args.size, args.size, generator=g)[:, rank * S_loc:(rank + 1) * S_loc]
+    images_host = torch.rand(args.scenes, args.views, 3, args.size, args.size, generator=g)[:, rank * S_loc:(rank + 1) * S_loc]
     images_host = images_host.contiguous().pin_memory()
     images_dev = images_host.to(dev)
 
@@ -294,18 +305,21 @@ def run_b200(args):
     if rank != 0:
         _finish(world)
         return
-    value = args.views / (ms * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+    n_views = args.scenes * args.views
+    value = n_views / (ms * 1e-3)
+    line = {"metric": METRIC if config_name(args) == "C2" else f"views/sec ({config_name(args)})", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "gpu_launches": launches, "cuda_graph": graphed,
-            "e2e": {"value": args.views / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e,
+            "e2e": {"value": n_views / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "kernel_shares": shares,
             "algorithmic_tflop_per_step": trunk_tflop(args)}
     line["model_flop_utilisation"] = {"achieved_tflops": line["algorithmic_tflop_per_step"] / (ms * 1e-3) / world,
                                       "peak_tflops": peaks["tflops"], "frac": line["algorithmic_tflop_per_step"] / (ms * 1e-3) / world / peaks["tflops"]}
     if world == 1 and not args.no_cpu_baseline:
+        if not args.part:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args, dt, images_dev)
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
     _finish(world)
@@ -336,7 +350,7 @@ def trunk_tflop(args):
     frame = 48 * 4 * T * T * 1024 / 1e12
     glob = 24 * 4 * T * (S * T) * 1024 / 1e12
     heads = 2 * 0.2180e-3 * g * g
-    return S * (lin + frame + glob + heads)
+    return args.scenes * S * (lin + frame + glob + heads)
 
 
 def cpu_threads():
@@ -344,6 +358,40 @@ def cpu_threads():
     128 threads on the 128-core bench host, 14 s with 8 threads on an 8-core box) well before 128 threads; the CPU
     legs use at most 32 and report that number as `cores`."""
     return max(1, min(os.cpu_count() or 1, 32))
+
+
+def gpu_eager_baseline(args, dt, images_dev):
+    """SURVEY 8(d)'s "real bar": the reference algorithm as PyTorch eager on THIS B200 - the oracle port with its
+    Linear / SDPA calls issued natively in the autocast dtype (ref_model.NATIVE_16BIT: cuBLAS 16-bit GEMMs, the
+    SDPA backend torch picks; heads fp32 with cuDNN TF32 convolutions, PyTorch's default), same inputs and config."""
+    from oracle import ref_model, weights  # checker used as a baseline (never on the product path)
+    sd = weights.make_state_dict(0, "default", prefixes=("aggregator.", "camera_head.", "depth_head.", "point_head."))
+    sd = {k: v.to(images_dev.device) for k, v in sd.items()}
+    ref_model.NATIVE_16BIT = True
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        for i in range(1 + reps):
+            if i == 1:
+                torch.cuda.synchronize()
+                e0.record()
+            ref_model.forward(sd, images_dev, model="vggt", amp=dt, skip_part=True, frames_chunk=8)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    finally:
+        ref_model.NATIVE_16BIT = False
+        ref_model._W16.clear()
+        torch.backends.cudnn.allow_tf32 = tf32
+        del sd
+        torch.cuda.empty_cache()
+    n = args.scenes * args.views
+    return {"value": n / (ms * 1e-3), "unit": "views/s", "ms_per_step": ms, "kind": "port",
+            "what": f"oracle port as PyTorch {torch.__version__} eager on the same GPU: {args.dtype} Linear / SDPA "
+                    "(cuBLAS + torch's SDPA backend), fp32 LayerNorm / residual, heads fp32 with cuDNN TF32 convolutions; "
+                    f"{reps} forwards after 1 warm-up, CUDA events; device-resident inputs"}
 
 
 def cpu_baseline(args):
@@ -359,7 +407,7 @@ def cpu_baseline(args):
     ref_model.forward(sd, images, model="vggt", skip_part=True, frames_chunk=2)
     dt = time.perf_counter() - t0
     return {"value": S / dt, "unit": "views/s", "cores": cores, "kind": "port",
-            "sample": f"one fp32 forward of {S} of the 8 views at {args.size}x{args.size} ({dt:.1f} s), oracle port, "
+            "sample": f"one fp32 forward of {S} of the {args.views} views at {args.size}x{args.size} ({dt:.1f} s), oracle port, "
                       f"{cores} threads"}
 
 
@@ -369,7 +417,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--views", type=int, default=8, help="views per scene")
+    ap.add_argument("--scenes", type=int, default=1, help="scenes per step (C5: 4)")
     ap.add_argument("--size", type=int, default=518)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--part", action="store_true", help="IGGT with the part path (needs an even patch grid, e.g. --size 532)")

@@ -11,6 +11,26 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from . import ops
+
+
+def _trace_begin():
+    """bench.py's per-kernel trace (ops.TRACE) also gets a row for the exchange step: CUDA events on the current stream
+    around the K|V staging copy + the collective (torch's NCCL work joins the current stream at both ends)."""
+    if ops.TRACE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _trace_end(e0, name, nbytes):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    ops.TRACE.append((name, 0.0, float(nbytes), e0, e1, ()))
+
 
 def make_kv_gather(group, world: int, B: int, S_loc: int, T: int):
     """Returns f(qkv[M_loc, 3072]) -> (K view, V view, Lk) over all ranks' tokens, scene-major."""
@@ -18,11 +38,13 @@ def make_kv_gather(group, world: int, B: int, S_loc: int, T: int):
 
     def gather(qkv: torch.Tensor):
         dev, dt = qkv.device, qkv.dtype
+        ev = _trace_begin()
         send = qkv[:, 1024:].contiguous()                                  # [M_loc, 2048]  (K | V)
         recv = torch.empty((world, M_loc, 2048), dtype=dt, device=dev)
         dist.all_gather_into_tensor(recv.view(world * M_loc, 2048), send, group=group)
         if B > 1:  # rows arrive (rank, scene, view, token); attention wants (scene, rank, view, token)
             recv = recv.view(world, B, S_loc * T, 2048).transpose(0, 1).contiguous()
+        _trace_end(ev, "nccl_all_gather_kv", (world + 1) * M_loc * 2048 * 2.0)
         kv = recv.view(world * M_loc, 2048)
         return kv[:, :1024], kv[:, 1024:], world * S_loc * T
 
@@ -35,8 +57,10 @@ def gather_camera_tokens(tokens23: torch.Tensor, group, world: int) -> torch.Ten
     if world == 1:
         return cam
     B, S_loc, C = cam.shape
+    ev = _trace_begin()
     recv = torch.empty((world, B, S_loc, C), dtype=cam.dtype, device=cam.device)
     dist.all_gather_into_tensor(recv.view(-1), cam.view(-1), group=group)
+    _trace_end(ev, "nccl_all_gather_camera_tokens", (world + 1) * cam.numel() * 4.0)
     return recv.permute(1, 0, 2, 3).reshape(B, world * S_loc, C).contiguous()
 
 
@@ -50,6 +74,19 @@ def shard_views(model, group=None):
     return model
 
 
+def _check_equal_shards(model, shape, group, world):
+    """`all_gather_into_tensor` needs the same [B, S_loc, 3, H, W] on every rank; verify it once per shape (a host-side
+    object all-gather, outside any CUDA-graph capture) and fail with a description instead of a hang / garbage."""
+    seen = model.__dict__.setdefault("_shard_shapes_ok", set())
+    if world <= 1 or shape in seen or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        return
+    shapes = [None] * world
+    dist.all_gather_object(shapes, shape, group=group)
+    if any(s != shape for s in shapes):
+        raise ValueError(f"view sharding needs the same number of views and the same image size on every rank, got {shapes}")
+    seen.add(shape)
+
+
 @torch.no_grad()
 def forward_sharded(model, images_local: torch.Tensor, rank: int, world: int, group=None):
     """images_local [B, S_loc, 3, H, W]: this rank's views.  Returns the prediction dict for the local
@@ -59,6 +96,7 @@ def forward_sharded(model, images_local: torch.Tensor, rank: int, world: int, gr
     if images_local.dim() == 4:
         images_local = images_local.unsqueeze(0)
     B, S_loc = images_local.shape[:2]
+    _check_equal_shards(model, tuple(images_local.shape), group, world)
     dt, hd = model._dtype(), model._head_dtype()
     tokens, psi = model.aggregator(images_local, compute_dtype=dt, view_offset=rank * S_loc,
                                    total_views=world * S_loc)

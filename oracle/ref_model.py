@@ -37,15 +37,34 @@ def _r(x, amp):
     return x if amp is None else x.to(amp).float()
 
 
+# NATIVE_16BIT: issue the autocast region's Linear / SDPA calls in the 16-bit dtype itself (what torch.amp.autocast does
+# on a GPU: cuBLAS 16-bit GEMMs with fp32 accumulation, the fused SDPA backends) instead of emulating the rounding
+# points with fp32 arithmetic.  Same rounding points, library summation order; only bench.py's `gpu_eager_baseline`
+# (the reference algorithm as PyTorch eager on the GPU) sets it.  _W16 mirrors autocast's weight-cast cache.
+NATIVE_16BIT = False
+_W16: Dict[int, torch.Tensor] = {}
+
+
+def _w16(w, amp):
+    t = _W16.get(id(w))
+    if t is None or t.dtype != amp:
+        t = _W16[id(w)] = w.to(amp)
+    return t
+
+
 def linear(x, w, b, amp=None):
     """nn.Linear under autocast: 16-bit operands, fp32 accumulate, 16-bit result."""
     if amp is None:
         return F.linear(x, w, b)
+    if NATIVE_16BIT:
+        return F.linear(x.to(amp), _w16(w, amp), None if b is None else _w16(b, amp)).float()
     return _r(F.linear(_r(x, amp), _r(w, amp), None if b is None else _r(b, amp)), amp)
 
 
 def sdpa(q, k, v, scale, amp=None, q_chunk=2048):
     """softmax(q k^T * scale) v, exact, fp32 math (F.scaled_dot_product_attention, attention.py:61-66)."""
+    if NATIVE_16BIT and amp is not None:
+        return F.scaled_dot_product_attention(q.to(amp), k.to(amp), v.to(amp), scale=scale).float()
     q, k, v = _r(q, amp), _r(k, amp), _r(v, amp)
     outs = []
     for s in range(0, q.shape[-2], q_chunk):
@@ -116,6 +135,9 @@ def attention(sd, pre, x, heads, qk_norm, pos, amp):
 
 def mlp(sd, pre, x, amp):
     """layers/mlp.py:34-40 (exact-erf GELU evaluated on the 16-bit fc1 output under autocast)"""
+    if NATIVE_16BIT and amp is not None:      # fc1 -> GELU -> fc2 stay 16-bit tensors, as under autocast on a GPU
+        h = F.gelu(F.linear(x.to(amp), _w16(sd[pre + "fc1.weight"], amp), _w16(sd[pre + "fc1.bias"], amp)))
+        return F.linear(h, _w16(sd[pre + "fc2.weight"], amp), _w16(sd[pre + "fc2.bias"], amp)).float()
     h = linear(x, sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], amp)
     h = _r(F.gelu(h), amp)
     return linear(h, sd[pre + "fc2.weight"], sd[pre + "fc2.bias"], amp)
