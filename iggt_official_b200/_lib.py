@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libiggt_b200.so")
+LIB_PATH = os.environ.get("IGGT_B200_LIB") or os.path.join(_HERE, "lib", "libiggt_b200.so")   # override: dev builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 _lib = None
@@ -31,6 +31,10 @@ SIGNATURES = {
                        c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "iggt_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                            c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "iggt_attention_plan": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iggt_attention_fwd_ws": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                              c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_int64, c_void_p],
+    "iggt_attention_schedule_splits": [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "iggt_layernorm": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int64,
                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "iggt_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -36,6 +36,7 @@ constexpr int A3_XCHG = 2 * 2 * 128 * 4;      // max / sum exchange: [tile][half
 constexpr int A3_SMEM = A3_TILE * (4 + 2 * A3_STAGES) + 2 * A3_P + A3_XCHG + 512;   // Q is double-buffered per tile
 static_assert(A3_SMEM <= 232448, "shared memory budget");
 constexpr float A3_TAU = 8.0f;                // lazy-rescale threshold in log2 units
+constexpr int A3_DEFAULT_EMU8 = 0;            // probability pairs (of every 8) on the FMA-pipe exp2 by default
 
 struct Attn3Params {
   int Lq, Lk, H, num_seq;
@@ -46,6 +47,12 @@ struct Attn3Params {
   float scale_log2;
   int stagger_at;       // tile A signals tile B's start after this many (x16) exps of its first kv tile (0..4)
   int light_tail;       // the last query pair of every (sequence, head) has no rows for tile B (Lq = 1374: 94 rows)
+  // split-KV (view-sharded ranks: 88 work items for 148 SMs): the kv tiles of every item are cut into `kv_splits` ranges
+  // of `tiles_per_split`; each (item, split) writes its un-normalised fp32 O and (m, l) to the workspace and
+  // attention3_merge_kernel combines the splits.  kv_splits == 1: the kernel writes the normalised 16-bit output itself.
+  int kv_splits, tiles_per_split;
+  float* ws_o;          // [split][num_seq * Lq][H * 64]
+  float* ws_ml;         // [split][num_seq * Lq][H][2]  (running max in log2-scaled units' source scale, row sum)
 };
 
 // Work items = (query-tile pair, head, sequence).  When the last pair of every (sequence, head) has no rows for tile B
@@ -59,10 +66,10 @@ struct Attn3Items {
   const Attn3Params& p;
   // G CTAs in the grid, this is CTA c (host-callable so that the schedule itself is unit-tested without a GPU)
   __host__ __device__ Attn3Items(const Attn3Params& p_, int G_, int c_) : p(p_) {
-    G = G_; c = c_; k = 0;
+    G = G_; c = c_; k = 0; split = 0;
     if (p.light_tail) {
       full_pairs = p.q_pairs - 1;
-      n_half = p.H * p.num_seq;
+      n_half = p.H * p.num_seq * p.kv_splits;
       n_full = full_pairs * n_half;
     } else {
       full_pairs = p.q_pairs; n_full = p.total_items; n_half = 0;
@@ -70,6 +77,7 @@ struct Attn3Items {
     r = n_full % G;
   }
   // next item of this CTA: false when done; b_active = tile B has rows
+  int split;      // kv split of the item returned last by next() / peek()
   __host__ __device__ bool next(int& qp, int& head, int& seq, bool& b_active) {
     const int my_full = (n_full - c + G - 1) / G;            // full items of this CTA (c, c + G, ...)
     int sh;
@@ -96,14 +104,21 @@ struct Attn3Items {
     }
     ++k;
     head = sh % p.H;
-    seq = sh / p.H;
+    const int rest = sh / p.H;
+    seq = rest % p.num_seq;
+    split = rest / p.num_seq;
     return true;
+  }
+  // kv tile range [j0, j1) of the current item
+  __host__ __device__ void kv_range(int n_kv, int& j0, int& j1) const {
+    j0 = split * p.tiles_per_split;
+    j1 = j0 + p.tiles_per_split < n_kv ? j0 + p.tiles_per_split : n_kv;
   }
   // the item that follows the current one (for the Q prefetch), without advancing
   __host__ __device__ bool peek(int& qp, int& head, int& seq, bool& b_active) {
-    const int k0 = k;
+    const int k0 = k, split0 = split;
     const bool ok = next(qp, head, seq, b_active);
-    k = k0;
+    k = k0; split = split0;
     return ok;
   }
 };
@@ -146,21 +161,35 @@ __device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool 
   return out != 0;
 }
 
-// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-3
-// Chebyshev polynomial for 2^f (max relative error 1.0e-4, below half an fp16 ulp of P), exponent patched in
-// with an integer add.  Used for EMU of every 4 probabilities to take load off the 16-op/clk/SM MUFU unit.
-__device__ __forceinline__ float ex2_emulated(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                 // 1.5 * 2^23
-  const float f = x - (t - 12582912.0f);
-  float pz = fmaf(0.05583828315138817f, f, 0.2426394820213318f);
-  pz = fmaf(pz, f, 0.6931367516517639f);
-  pz = fmaf(pz, f, 0.9999245405197144f);
-  return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+// 2^x for TWO values at once on the FMA / ALU pipes (no MUFU), with the sm_100 packed-fp32 instructions: Cody-Waite split
+// x = n + f with the 1.5 * 2^23 magic-number add (FADD2), f = x - n (FADD2 + FFMA2), a degree-3 polynomial for 2^f on
+// [-0.5, 0.5] (3 FFMA2, max relative error 1.0e-4 - below half an fp16 ulp of P), and the exponent patched in with one
+// shift-add per value.  5.5 issue slots per value against 1.5 for the MUFU path (the scale-and-shift FFMA2 is shared),
+// but the MUFU unit retires only 4 lanes / clk / sub-partition (8 clk per warp instruction): moving EMU8 of every 8
+// probability pairs here trades idle issue slots for MUFU time.  x may be -inf (masked keys): clamped to -126.
+__device__ __forceinline__ float2 ex2_emulated2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);          // 1.5 * 2^23
+  const float2 t = fadd2(x, magic);                                      // low mantissa bits of t = round(x)
+  const float2 r = fadd2(t, make_float2(-12582912.0f, -12582912.0f));    // round(x), exact
+  const float2 f = ffma2(r, make_float2(-1.0f, -1.0f), x);               // x - round(x) in [-0.5, 0.5], exact
+  float2 pz = ffma2(make_float2(0.05583828315138817f, 0.05583828315138817f), f,
+                    make_float2(0.2426394820213318f, 0.2426394820213318f));
+  pz = ffma2(pz, f, make_float2(0.6931367516517639f, 0.6931367516517639f));
+  pz = ffma2(pz, f, make_float2(0.9999245405197144f, 0.9999245405197144f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23));
+  y.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23));
+  return y;
+}
+// which of the 32 probability pairs of a thread's 64 keys go through ex2_emulated2: EMU8 of every 8, evenly spread
+__host__ __device__ constexpr bool emu_pair(int pair, int emu8) {
+  return ((pair % 8) * emu8) / 8 != (((pair % 8) + 1) * emu8) / 8;
 }
 
 // PT: P goes to TMEM (tcgen05.st, consumed as the A operand of P V straight from tensor memory) instead of shared memory.
-template <bool BF16, int EMU, bool PT>
+template <bool BF16, int EMU8, bool PT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
@@ -243,9 +272,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       bool b_active, nb;
       if (items.peek(qp, head, seq, b_active)) load_q(qp, head, seq, b_active);
       while (items.next(qp, head, seq, b_active)) {
+        int j0, j1;
+        items.kv_range(n_kv, j0, j1);
         const bool has_next = items.peek(nqp, nhead, nseq, nb);
         const int col = head * A3_D;
-        for (int j = 0; j < n_kv; ++j) {
+        for (int j = j0; j < j1; ++j) {
           const int row = seq * p.Lk + j * A3_BK;
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_expect_tx(&k_full[st], A3_TILE);
@@ -254,7 +285,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_expect_tx(&v_full[st], A3_TILE);
           tma_load_2d(sV + st * A3_TILE, &tmV, &v_full[st], col, row);
           if (++st == A3_STAGES) { st = 0; ph ^= 1; }
-          if (j == 0 && has_next) load_q(nqp, nhead, nseq, nb);
+          if (j == j0 && has_next) load_q(nqp, nhead, nseq, nb);
         }
       }
     } else if ((warp == 1 || warp == 3) && lane == 0) {
@@ -276,10 +307,13 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int qp_, head_, seq_;
       bool b_active;
       while (items.next(qp_, head_, seq_, b_active)) {
+        int j0_, j1_;
+        items.kv_range(n_kv, j0_, j1_);
+        const int n_it = j1_ - j0_;                          // kv tiles of this item (its split of the kv range)
         if (!b_active && t == 1) {
           // tile B has no rows in this item: only keep the shared K/V ring turning (its stages are released by
           // BOTH tiles; waiting for `full` first keeps this thread from arriving twice in one phase)
-          for (int j = 0; j < n_kv; ++j) {
+          for (int j = 0; j < n_it; ++j) {
             mbar_wait(&k_full[kst], kph);
             mbar_arrive(&k_empty[kst]);
             if (++kst == A3_STAGES) { kst = 0; kph ^= 1; }
@@ -295,9 +329,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t q_addr = smem_u32(sQ + (qbuf * 2 + t) * A3_TILE);
         mbar_wait(&q_full[qbuf * 2 + t], qbpar);
         if (t == 1) mbar_wait(stagger, qpar);
-        for (int j = -1; j < n_kv; ++j) {
+        for (int j = -1; j < n_it; ++j) {
           // S(j+1): as soon as the softmax warps have pulled S(j) into registers
-          if (j + 1 < n_kv) {
+          if (j + 1 < n_it) {
             mbar_wait(&k_full[kst], kph);
             mbar_wait(&s_empty[t], (qk_cnt & 1) ^ 1);
             tc_fence_after();
@@ -359,8 +393,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     bool b_active;
     while (items.next(qp, head, seq, b_active)) {
       if (!b_active && t == 1) continue;                             // no rows for tile B in this item
+      int j0, j1;
+      items.kv_range(n_kv, j0, j1);
+      const int split = items.split;
       float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < n_kv; ++j, ++kv_cnt) {
+      for (int j = j0; j < j1; ++j, ++kv_cnt) {
         mbar_wait(&s_full[t], kv_cnt & 1);
         tc_fence_after();
         float s[64];
@@ -393,7 +430,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           *xm = mloc;
           named_bar_sync(bar_id, 256);
           const float m_new = fmaxf(m, fmaxf(mloc, *xo));
-          if (j > 0) {
+          if (j > j0) {
             const float f = ex2_approx((m - m_new) * c);
             mbar_wait(&o_full[t], (kv_cnt - 1) & 1);       // P(j-1) V(j-1) has landed
             tc_fence_after();
@@ -417,7 +454,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // issue slots -- the softmax warps are bound by issue slots and MUFU, not by the FMA pipe
         float2 sum01 = make_float2(0.f, 0.f), sum23 = make_float2(0.f, 0.f);
         const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
-        const bool sig = (t == 0 && j == 0);
+        const bool sig = (t == 0 && j == j0);
         if (sig && p.stagger_at == 0) mbar_arrive(stagger);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -425,10 +462,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int i = q4 * 16; i < q4 * 16 + 16; i += 4) {
             float2 a = ffma2(make_float2(s[i], s[i + 1]), c2, nmc2);
             float2 b = ffma2(make_float2(s[i + 2], s[i + 3]), c2, nmc2);
-            a.x = EMU >= 1 ? ex2_emulated(a.x) : ex2_approx(a.x);
-            a.y = ex2_approx(a.y);
-            b.x = EMU >= 2 ? ex2_emulated(b.x) : ex2_approx(b.x);
-            b.y = ex2_approx(b.y);
+            if (emu_pair(i / 2, EMU8)) a = ex2_emulated2(a);
+            else { a.x = ex2_approx(a.x); a.y = ex2_approx(a.y); }
+            if (emu_pair(i / 2 + 1, EMU8)) b = ex2_emulated2(b);
+            else { b.x = ex2_approx(b.x); b.y = ex2_approx(b.y); }
             s[i] = a.x; s[i + 1] = a.y; s[i + 2] = b.x; s[i + 3] = b.y;
             sum01 = fadd2(sum01, a);
             sum23 = fadd2(sum23, b);
@@ -469,10 +506,22 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_arrive(&o_free[t]);
       *xm = l;
       named_bar_sync(bar_id, 256);
-      const float inv = 1.0f / (l + *xo);
+      const float l_tot = l + *xo;
+      const float inv = 1.0f / l_tot;
       named_bar_sync(bar_id, 256);                         // slots are reused by the next item's first tile
       const int qrow = (qp * 2 + t) * A3_BQ + row;
-      if (qrow < p.Lq) {
+      if (p.kv_splits > 1) {
+        // partial result of this kv split: un-normalised O (relative to this split's running max m) + (m, l)
+        if (qrow < p.Lq) {
+          const int64_t grow = static_cast<int64_t>(split) * p.num_seq * p.Lq + static_cast<int64_t>(seq) * p.Lq + qrow;
+          float4* dst = reinterpret_cast<float4*>(p.ws_o + grow * (p.H * A3_D) + head * A3_D + h * 32);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            dst[ch] = make_float4(__uint_as_float(r[ch * 4]), __uint_as_float(r[ch * 4 + 1]), __uint_as_float(r[ch * 4 + 2]),
+                                  __uint_as_float(r[ch * 4 + 3]));
+          if (h == 0) *reinterpret_cast<float2*>(p.ws_ml + (grow * p.H + head) * 2) = make_float2(m, l_tot);
+        }
+      } else if (qrow < p.Lq) {
         uint16_t* dst = reinterpret_cast<uint16_t*>(p.o) + (static_cast<int64_t>(seq) * p.Lq + qrow) * p.ldo +
                         head * A3_D + h * 32;
 #pragma unroll
@@ -496,10 +545,41 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <bool BF16, int EMU, bool PT>
+// Combines the kv splits of attention3_kernel: one warp per (query row, head), lane = two of the 64 columns.
+//   m = max_s m_s,  w_s = 2^((m_s - m) * scale_log2),  out = sum_s w_s O_s / sum_s w_s l_s
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+attention3_merge_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, void* __restrict__ out, int64_t ldo,
+                        int64_t rows, int H, int splits, float scale_log2) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;     // (row, head)
+  if (item >= rows * H) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = item / H;
+  const int head = static_cast<int>(item % H);
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, __ldg(ws_ml + ((s * rows + row) * H + head) * 2));
+  float2 acc = make_float2(0.f, 0.f);
+  float l = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 ml = __ldg(reinterpret_cast<const float2*>(ws_ml + ((s * rows + row) * H + head) * 2));
+    const float w = ex2_approx((ml.x - m) * scale_log2);
+    const float2 o = __ldg(reinterpret_cast<const float2*>(ws_o + (s * rows + row) * (static_cast<int64_t>(H) * A3_D) +
+                                                             head * A3_D + lane * 2));
+    acc.x = fmaf(w, o.x, acc.x);
+    acc.y = fmaf(w, o.y, acc.y);
+    l = fmaf(w, ml.y, l);
+  }
+  const float inv = 1.0f / l;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(out) + row * ldo + head * A3_D + lane * 2);
+  *dst = pack16x2<BF16>(acc.x * inv, acc.y * inv);
+}
+
+template <bool BF16, int EMU8, bool PT>
 int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const Attn3Params& p,
                       cudaStream_t stream) {
-  auto kern = attention3_kernel<BF16, EMU, PT>;
+  auto kern = attention3_kernel<BF16, EMU8, PT>;
   static DeviceOnce once;
   if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
@@ -515,11 +595,54 @@ int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtens
 using namespace iggt;
 
 namespace {
-void attn3_shape(Attn3Params& p, int num_seq, int Lq, int Lk, int H) {
+// Cost (in kv-tile steps of one CTA) of running the launch with `splits` kv ranges on `sms` CTAs: rounds x (tiles per
+// split + a fixed per-item overhead: Q load, first-tile max, O read-out) + the merge pass over the fp32 workspace.
+double attn3_cost(int num_seq, int Lq, int Lk, int H, int splits, int sms) {
+  const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ, n_kv = (Lk + A3_BK - 1) / A3_BK;
+  const int tps = (n_kv + splits - 1) / splits, se = (n_kv + tps - 1) / tps;
+  const double full = static_cast<double>(num_seq) * H * (q_tiles / 2) * se;       // items with both query tiles
+  const double half = (q_tiles & 1) ? static_cast<double>(num_seq) * H * se : 0.0;  // items whose tile B has no rows
+  const double weight = full + 0.5 * half;
+  double rounds;
+  if (full + half <= sms) rounds = full > 0 ? 1.0 : 0.5;
+  else {   // longest-first: the busiest CTA carries ceil(full / sms) full items, or the average rounded up to a half item
+    const double by_weight = static_cast<double>(static_cast<long>(2.0 * weight / sms + 0.999999)) / 2.0;
+    const double by_full = static_cast<double>(static_cast<long>(full / sms + 0.999999));
+    rounds = by_weight > by_full ? by_weight : by_full;
+  }
+  double cost = rounds * (tps + 2.0);
+  if (se > 1) {
+    const double ws_bytes = 2.0 * se * num_seq * Lq * H * A3_D * 4;     // written + read back
+    cost += 2.0 + ws_bytes / 4.0e12 / 1.36e-6;                           // ~4 TB/s through L2, 1.36 us per kv-tile step
+  }
+  return cost;
+}
+// kv splits that minimise attn3_cost (1 = no split); IGGT_ATTN_SPLITS forces a value
+int attn3_plan_splits(int num_seq, int Lq, int Lk, int H, int sms) {
+  static const int forced = [] { const char* e = getenv("IGGT_ATTN_SPLITS"); return e ? atoi(e) : 0; }();
+  const int n_kv = (Lk + A3_BK - 1) / A3_BK;
+  int best = 1;
+  if (forced > 0) {
+    best = forced < n_kv ? forced : n_kv;
+  } else {
+    double bc = attn3_cost(num_seq, Lq, Lk, H, 1, sms);
+    for (int s = 2; s <= 8 && s <= n_kv; ++s) {
+      const double c = attn3_cost(num_seq, Lq, Lk, H, s, sms);
+      if (c < 0.93 * bc) { bc = c; best = s; }        // a split must buy at least 7 %
+    }
+  }
+  const int tps = (n_kv + best - 1) / best;
+  return (n_kv + tps - 1) / tps;                       // effective splits (no empty range)
+}
+void attn3_shape(Attn3Params& p, int num_seq, int Lq, int Lk, int H, int splits = 1) {
   p.Lq = Lq; p.Lk = Lk; p.H = H; p.num_seq = num_seq;
   const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ;
+  const int n_kv = (Lk + A3_BK - 1) / A3_BK;
   p.q_pairs = (q_tiles + 1) / 2;
-  p.total_items = num_seq * H * p.q_pairs;
+  p.kv_splits = splits < 1 ? 1 : splits;
+  p.tiles_per_split = (n_kv + p.kv_splits - 1) / p.kv_splits;
+  p.ws_o = nullptr; p.ws_ml = nullptr;
+  p.total_items = num_seq * H * p.q_pairs * p.kv_splits;
   static const int lpt = [] { const char* e = getenv("IGGT_ATTN_LPT"); return e ? atoi(e) : 1; }();
   p.light_tail = (lpt && (q_tiles & 1) && p.q_pairs > 1) ? 1 : 0;    // odd tile count: the last pair has no tile B
 }
@@ -545,11 +668,33 @@ extern "C" int iggt_attention_schedule(int num_seq, int Lq, int Lk, int H, int g
   return n;
 }
 
-extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                                  int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
-                                  int head_dim, float scale, int dtype, iggt_stream_t stream) {
+// As iggt_attention_schedule, for a launch with `splits` kv ranges: quintuples (query pair, head, sequence, tile-B-active,
+// kv split); also returns the kv tiles per split through *tiles_per_split.
+extern "C" int iggt_attention_schedule_splits(int num_seq, int Lq, int Lk, int H, int splits, int grid, int cta, int* items,
+                                              int max_items, int* tiles_per_split) {
+  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || splits <= 0 || grid <= 0 || cta < 0 || cta >= grid) return -1;
+  Attn3Params p{};
+  attn3_shape(p, num_seq, Lq, Lk, H, splits);
+  if (tiles_per_split) *tiles_per_split = p.tiles_per_split;
+  Attn3Items it(p, grid, cta);
+  int n = 0, qp, head, seq;
+  bool b_active;
+  while (it.next(qp, head, seq, b_active)) {
+    if (items && n < max_items) {
+      items[5 * n] = qp; items[5 * n + 1] = head; items[5 * n + 2] = seq; items[5 * n + 3] = b_active ? 1 : 0;
+      items[5 * n + 4] = it.split;
+    }
+    ++n;
+  }
+  return n;
+}
+
+namespace {
+int attention_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, int num_seq, int Lq, int Lk, int H, int head_dim, float scale, int dtype, int splits,
+                     void* ws, int64_t ws_bytes, cudaStream_t s) {
   if (head_dim != 64) return -1;
-  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0) return -1;
+  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || splits < 1) return -1;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -2;
   if (dtype != 0 && dtype != 1) return -3;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
@@ -558,19 +703,59 @@ extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int
   if (make_tmap_2d(&tK, dt, k, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldk, 64, A3_BK)) return -4;
   if (make_tmap_2d(&tV, dt, v, (uint64_t)num_seq * Lk, (uint64_t)H * 64, ldv, 64, A3_BK)) return -4;
   Attn3Params p;
-  attn3_shape(p, num_seq, Lq, Lk, H);
+  attn3_shape(p, num_seq, Lq, Lk, H, splits);
+  const int n_kv = (Lk + A3_BK - 1) / A3_BK;
+  if ((p.kv_splits - 1) * p.tiles_per_split >= n_kv) return -5;        // an empty kv range: use iggt_attention_plan's count
+  const int64_t rows = static_cast<int64_t>(num_seq) * Lq;
+  if (p.kv_splits > 1) {
+    const int64_t need = p.kv_splits * rows * H * (A3_D + 2) * 4;
+    if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) return -6;
+    p.ws_o = reinterpret_cast<float*>(ws);
+    p.ws_ml = p.ws_o + p.kv_splits * rows * H * A3_D;
+  }
   p.ldo = ldo; p.o = o;
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int stag = [] { const char* e = getenv("IGGT_ATTN_STAG"); return e ? atoi(e) : 2; }();
   p.stagger_at = stag < 0 ? 0 : (stag > 4 ? 4 : stag);
-  static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); return e ? atoi(e) : 0; }();
+  // IGGT_ATTN_EMU = how many of every 8 probability pairs take the FMA-pipe exp2 (0..4); IGGT_ATTN_PT=0 keeps P in
+  // shared memory (the pre-TMEM variant, MUFU only)
+  static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); int v = e ? atoi(e) : A3_DEFAULT_EMU8; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
   static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 1; }();
-  cudaStream_t s = (cudaStream_t)stream;
-  if (pt) {
-    if (emu == 1) return dtype ? launch_attention3<true, 1, true>(tQ, tK, tV, p, s) : launch_attention3<false, 1, true>(tQ, tK, tV, p, s);
-    return dtype ? launch_attention3<true, 0, true>(tQ, tK, tV, p, s) : launch_attention3<false, 0, true>(tQ, tK, tV, p, s);
+  int st;
+  if (!pt) st = dtype ? launch_attention3<true, 0, false>(tQ, tK, tV, p, s) : launch_attention3<false, 0, false>(tQ, tK, tV, p, s);
+  else switch (emu) {
+    case 1: st = dtype ? launch_attention3<true, 1, true>(tQ, tK, tV, p, s) : launch_attention3<false, 1, true>(tQ, tK, tV, p, s); break;
+    case 2: st = dtype ? launch_attention3<true, 2, true>(tQ, tK, tV, p, s) : launch_attention3<false, 2, true>(tQ, tK, tV, p, s); break;
+    case 3: st = dtype ? launch_attention3<true, 3, true>(tQ, tK, tV, p, s) : launch_attention3<false, 3, true>(tQ, tK, tV, p, s); break;
+    case 4: st = dtype ? launch_attention3<true, 4, true>(tQ, tK, tV, p, s) : launch_attention3<false, 4, true>(tQ, tK, tV, p, s); break;
+    default: st = dtype ? launch_attention3<true, 0, true>(tQ, tK, tV, p, s) : launch_attention3<false, 0, true>(tQ, tK, tV, p, s);
   }
-  if (emu == 1) return dtype ? launch_attention3<true, 1, false>(tQ, tK, tV, p, s) : launch_attention3<false, 1, false>(tQ, tK, tV, p, s);
-  if (emu == 2) return dtype ? launch_attention3<true, 2, false>(tQ, tK, tV, p, s) : launch_attention3<false, 2, false>(tQ, tK, tV, p, s);
-  return dtype ? launch_attention3<true, 0, false>(tQ, tK, tV, p, s) : launch_attention3<false, 0, false>(tQ, tK, tV, p, s);
+  if (st != 0 || p.kv_splits == 1) return st;
+  const int64_t warps = rows * H;
+  const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+  if (dtype) return (int)launch_pdl(attention3_merge_kernel<true>, dim3(grid), dim3(256), 0, s, (const float*)p.ws_o, (const float*)p.ws_ml, o, ldo, rows, H, p.kv_splits, p.scale_log2);
+  return (int)launch_pdl(attention3_merge_kernel<false>, dim3(grid), dim3(256), 0, s, (const float*)p.ws_o, (const float*)p.ws_ml, o, ldo, rows, H, p.kv_splits, p.scale_log2);
+}
+}  // namespace
+
+extern "C" int iggt_attention_plan(int num_seq, int Lq, int Lk, int H, int sms, int* splits, int64_t* ws_bytes) {
+  if (num_seq <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || !splits || !ws_bytes) return -1;
+  const int s = attn3_plan_splits(num_seq, Lq, Lk, H, sms > 0 ? sms : device_sm_count());
+  *splits = s;
+  *ws_bytes = s > 1 ? static_cast<int64_t>(s) * num_seq * Lq * H * (A3_D + 2) * 4 : 0;
+  return 0;
+}
+
+extern "C" int iggt_attention_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                     void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H, int head_dim, float scale,
+                                     int dtype, int splits, void* ws, int64_t ws_bytes, iggt_stream_t stream) {
+  return attention_launch(q, ldq, k, ldk, v, ldv, o, ldo, num_seq, Lq, Lk, H, head_dim, scale, dtype, splits, ws, ws_bytes,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                  int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
+                                  int head_dim, float scale, int dtype, iggt_stream_t stream) {
+  return attention_launch(q, ldq, k, ldk, v, ldv, o, ldo, num_seq, Lq, Lk, H, head_dim, scale, dtype, 1, nullptr, 0,
+                          (cudaStream_t)stream);
 }

@@ -141,16 +141,45 @@ def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None
     return out
 
 
-def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None):
-    """q/k/v: 2-D (possibly column-sliced) views [rows, H*64] with unit inner stride."""
+_ATTN_PLANS = {}
+
+
+def attention_plan(num_seq, Lq, Lk, H, sms=0):
+    """(kv splits, workspace bytes) the library picks for this shape (host-side, cached): > 1 only when the launch has
+    too few (sequence, head, query-tile) items for the SMs - the view-sharded global attention."""
+    import ctypes
+    key = (num_seq, Lq, Lk, H, sms)
+    if key not in _ATTN_PLANS:
+        s, b = ctypes.c_int(0), ctypes.c_int64(0)
+        _lib.check(_lib.load().iggt_attention_plan(num_seq, Lq, Lk, H, sms, ctypes.addressof(s), ctypes.addressof(b)),
+                   "iggt_attention_plan")
+        _ATTN_PLANS[key] = (s.value, b.value)
+    return _ATTN_PLANS[key]
+
+
+def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None, splits=None):
+    """q/k/v: 2-D (possibly column-sliced) views [rows, H*64] with unit inner stride.  `splits` (None = the library's
+    plan) > 1 runs the split-KV form with a torch-allocated fp32 workspace."""
     for t in (q, k, v):
         _chk2d(t)
     if out is None:
         out = torch.empty((num_seq * Lq, H * 64), dtype=q.dtype, device=q.device)
-    _call(q, "iggt_attention_fwd", 4.0 * num_seq * Lq * Lk * H * 64, 2.0 * num_seq * H * 64 * (2 * Lq + 2 * Lk),
-          q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
-                                        v.stride(0), out.data_ptr(), out.stride(0), num_seq, Lq, Lk, H, 64,
-                                        float(scale), _dt(q), _STREAM)
+    if splits is None:
+        splits, ws_bytes = attention_plan(num_seq, Lq, Lk, H)
+    else:
+        ws_bytes = splits * num_seq * Lq * H * 66 * 4 if splits > 1 else 0
+    flops, nbytes = 4.0 * num_seq * Lq * Lk * H * 64, 2.0 * num_seq * H * 64 * (2 * Lq + 2 * Lk)
+    if splits <= 1:
+        _call(q, "iggt_attention_fwd", flops, nbytes,
+              q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+              v.stride(0), out.data_ptr(), out.stride(0), num_seq, Lq, Lk, H, 64,
+              float(scale), _dt(q), _STREAM)
+    else:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+        _call(q, "iggt_attention_fwd_ws", flops, nbytes + 2.0 * ws_bytes,
+              q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+              v.stride(0), out.data_ptr(), out.stride(0), num_seq, Lq, Lk, H, 64,
+              float(scale), _dt(q), splits, ws.data_ptr(), ws_bytes, _STREAM)
     return out
 
 

@@ -74,6 +74,19 @@ int iggt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int64_t ldv, void* o, int64_t ldo, int num_seq, int Lq, int Lk, int H,
                        int head_dim, float scale, int dtype, iggt_stream_t stream);
 
+/* Split-KV form of iggt_attention_fwd for launches with fewer work items than SMs (view-sharded ranks: local queries
+ * against the gathered keys).  iggt_attention_plan picks the number of kv ranges for the shape (1 = do not split;
+ * sms <= 0: the current device's SM count) and the fp32 workspace it needs; iggt_attention_fwd_ws runs the flash kernel
+ * per (item, kv range) into the workspace (un-normalised O, running max, row sum) and merges the ranges.
+ * Same reference call site: F.scaled_dot_product_attention, iggt/layers/attention.py:61-66. */
+int iggt_attention_plan(int num_seq, int Lq, int Lk, int H, int sms, int* splits, int64_t* ws_bytes);
+int iggt_attention_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                          int64_t ldo, int num_seq, int Lq, int Lk, int H, int head_dim, float scale, int dtype,
+                          int splits, void* ws, int64_t ws_bytes, iggt_stream_t stream);
+/* Host-side view of the split launch's static schedule (no GPU needed): see iggt_attention_schedule. */
+int iggt_attention_schedule_splits(int num_seq, int Lq, int Lk, int H, int splits, int grid, int cta, int* items,
+                                   int max_items, int* tiles_per_split);
+
 /* ---- HBM-bound trunk kernels. */
 
 /* LayerNorm over C (1024 or 2048) fp32 features, one warp per row.  Output row g*out_rows_per_group +

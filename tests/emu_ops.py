@@ -35,7 +35,7 @@ def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
     return x
 
 
-def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None):
+def attention(q, k, v, num_seq, Lq, Lk, H, scale=0.125, out=None, splits=None):
     q4 = q.float().reshape(num_seq, Lq, H, 64).transpose(1, 2)
     k4 = k.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)
     v4 = v.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)

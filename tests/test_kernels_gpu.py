@@ -164,6 +164,64 @@ def test_attention(ops, dtype, num_seq, Lq, Lk, H):
     # P is rounded to 16 bit before PV (as in every flash kernel): 2 ulp of the output scale
     assert _relmax(out, ref) < 3 * _tol(dtype)
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("num_seq,Lq,Lk,H,splits", [(1, 1374, 10992, 16, 3), (1, 1374, 10992, 16, 5), (2, 300, 1000, 4, 2),
+                                                    (1, 129, 257, 2, 3), (3, 64, 700, 1, 6), (1, 2748, 10992, 16, 2)])
+def test_attention_split_kv(ops, dtype, num_seq, Lq, Lk, H, splits):
+    """Split-KV launches (view-sharded ranks): every (item, kv range) writes un-normalised O and (m, l) to the workspace,
+    the merge kernel combines them - must equal the exact softmax and the unsplit launch."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    C = H * 64
+    q = torch.randn(num_seq * Lq, C, device="cuda", generator=g).to(dtype)
+    kv = torch.randn(num_seq * Lk, 2 * C, device="cuda", generator=g).to(dtype)
+    kv[: Lk // 3] *= 4.0                                   # the running max of the first range is not the global one
+    k, v = kv[:, :C], kv[:, C:]
+    out = ops.attention(q, k, v, num_seq, Lq, Lk, H, splits=splits)
+    one = ops.attention(q, k, v, num_seq, Lq, Lk, H, splits=1)
+    torch.cuda.synchronize()
+    q4 = q.float().view(num_seq, Lq, H, 64).transpose(1, 2)
+    k4 = k.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)
+    v4 = v.float().reshape(num_seq, Lk, H, 64).transpose(1, 2)
+    ref = (torch.softmax(q4 @ k4.transpose(-1, -2) * 0.125, -1) @ v4).transpose(1, 2).reshape(num_seq * Lq, C)
+    assert _relmax(out, ref) < 3 * _tol(dtype)
+    assert _relmax(out, one.float()) < 2 * _tol(dtype)
+
+
+def test_attention_plan_is_used_and_cached(ops):
+    s, ws = ops.attention_plan(1, 1374, 10992, 16)
+    assert s >= 1 and (ws > 0) == (s > 1) and ops.attention_plan(1, 1374, 10992, 16) == (s, ws)
+    assert ops.attention_plan(8, 1374, 1374, 16)[0] == 1
+
+
+@pytest.mark.parametrize("emu", [0, 1, 2, 3, 4])
+def test_attention_emulated_exp2_variants(emu):
+    """IGGT_ATTN_EMU (probability pairs per 8 on the packed FMA-pipe exp2) is read once per process: each variant runs
+    in a child process against the exact softmax, incl. a ragged last kv tile and a split-KV launch."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from iggt_official_b200 import ops
+torch.manual_seed(3)
+for dt, tol in ((torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)):
+    for ns, Lq, Lk, H, sp in ((2, 300, 1374, 4, 1), (1, 1374, 2748, 16, 2), (3, 64, 64, 2, 1)):
+        q = torch.randn(ns * Lq, H * 64, device="cuda").to(dt)
+        kv = (torch.randn(ns * Lk, 2 * H * 64, device="cuda") * 1.5).to(dt)
+        out = ops.attention(q, kv[:, :H * 64], kv[:, H * 64:], ns, Lq, Lk, H, splits=sp)
+        q4 = q.float().view(ns, Lq, H, 64).transpose(1, 2)
+        k4 = kv[:, :H * 64].float().reshape(ns, Lk, H, 64).transpose(1, 2)
+        v4 = kv[:, H * 64:].float().reshape(ns, Lk, H, 64).transpose(1, 2)
+        ref = (torch.softmax(q4 @ k4.transpose(-1, -2) * 0.125, -1) @ v4).transpose(1, 2).reshape(ns * Lq, H * 64)
+        err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+        assert err < 3 * tol, (str(dt), ns, Lq, Lk, H, sp, err)
+print("EMU_OK")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, IGGT_ATTN_EMU=str(emu)), capture_output=True,
+                       text=True, timeout=300)
+    assert "EMU_OK" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
 
 @pytest.mark.parametrize("out_dtype", [torch.float16, torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("C", [1024, 2048])

@@ -99,3 +99,63 @@ def test_schedule_argument_errors():
     lib = _lib.load()
     assert lib.iggt_gemm_plan(7, 1, 1, 1, None) < 0
     assert lib.iggt_attention_schedule(1, 128, 128, 1, 4, 4, None, 0) < 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# split-KV launches (view-sharded global attention: local queries against the gathered keys)
+def _plan(num_seq, Lq, Lk, H, sms=SMS):
+    import ctypes
+    s, b = ctypes.c_int(0), ctypes.c_int64(0)
+    assert _lib.load().iggt_attention_plan(num_seq, Lq, Lk, H, sms, ctypes.addressof(s), ctypes.addressof(b)) == 0
+    return s.value, b.value
+
+
+def _schedule_splits(num_seq, Lq, Lk, H, splits, grid, cta):
+    import ctypes
+    buf = (ctypes.c_int * (5 * 4096))()
+    tps = ctypes.c_int(0)
+    n = _lib.load().iggt_attention_schedule_splits(num_seq, Lq, Lk, H, splits, grid, cta, ctypes.addressof(buf), 4096,
+                                                   ctypes.addressof(tps))
+    assert 0 <= n <= 4096
+    return [tuple(buf[5 * i:5 * i + 5]) for i in range(n)], tps.value
+
+
+def test_attention_plan_splits_only_when_items_are_scarce():
+    # one GPU, C2: plenty of items -> never split (the workspace traffic would cost more than the tail it balances)
+    assert _plan(8, 1374, 1374, 16) == (1, 0)
+    assert _plan(1, 8 * 1374, 8 * 1374, 16) == (1, 0)
+    # 8 GPUs, C2: 1 view per rank = 96 items for 148 SMs, 86 kv tiles each -> split the kv range
+    s, ws = _plan(1, 1374, 8 * 1374, 16)
+    assert 3 <= s <= 8 and ws == s * 1374 * 16 * 66 * 4
+    # 4 / 2 GPUs
+    assert _plan(1, 2 * 1374, 8 * 1374, 16)[0] >= 2
+    # C3 on 8 GPUs: 4 views per rank against 32 views of keys
+    s3, _ = _plan(1, 4 * 1374, 32 * 1374, 16)
+    assert s3 >= 1
+    # a split never leaves an empty kv range
+    for Lk in (128, 129, 300, 1374, 10992):
+        for forced in range(1, 9):
+            n_kv = -(-Lk // 128)
+            tps = -(-n_kv // forced)
+            assert (-(-n_kv // tps) - 1) * tps < n_kv
+
+
+def test_split_schedule_covers_every_item_and_range_once():
+    num_seq, Lq, Lk, H, splits = 1, 1374, 8 * 1374, 16, 3
+    q_pairs = (-(-Lq // 128) + 1) // 2
+    n_kv = -(-Lk // 128)
+    seen, loads = set(), []
+    for cta in range(SMS):
+        items, tps = _schedule_splits(num_seq, Lq, Lk, H, splits, SMS, cta)
+        assert tps == -(-n_kv // splits)
+        load = 0.0
+        for qp, head, seq, b_active, split in items:
+            assert 0 <= split < splits and (qp, head, seq, split) not in seen
+            seen.add((qp, head, seq, split))
+            load += (1.0 if b_active else 0.5) * (min(n_kv, (split + 1) * tps) - split * tps)
+        loads.append(load)
+    assert len(seen) == num_seq * H * q_pairs * splits
+    covered = sum(min(n_kv, (s + 1) * tps) - s * tps for s in range(splits))
+    assert covered == n_kv                                             # the ranges tile [0, n_kv)
+    # 96 items x 86 tiles on one GPU of eight: unsplit the busiest CTA runs 86 tile steps; split in three, 58
+    assert max(loads) <= 2 * tps
