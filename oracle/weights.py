@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- seeded synthetic checkpoints with the reference's exact `state_dict` layout.
 
 No IGGT checkpoint is reachable offline (weights live on the HF hub, README.md:10), so parity is checked on
-synthetic weights.  `state_manifest.json` (names / shapes / dtypes of `IGGT().state_dict()`, 2053 entries,
-written by oracle/make_manifest.py from the unmodified reference) defines the layout; this module fills it
-deterministically on CPU so the GPU box can rebuild the very same weights without /root/reference.
+synthetic weights.  The layout (names / shapes / dtypes of `IGGT().state_dict()`, 2053 entries) is the schema file
+iggt_official_b200/state_layout.json, pinned to the unmodified reference by the digest oracle/make_manifest.py records
+(oracle/state_manifest.sha256.json, checked in tests/test_layout.py); this module fills it deterministically on CPU so
+the GPU box can rebuild the very same weights without /root/reference.
 
 kind="default": magnitudes follow the reference initialisers (LayerScale 0.01 in the aggregator / camera
 trunk, 1.0 in DINOv2; aggregator.py:63,153).  kind="stress": LayerScale ~ U(0.5, 1.5) and non-trivial LayerNorm
@@ -16,7 +17,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-MANIFEST = os.path.join(_HERE, "state_manifest.json")
+MANIFEST = os.path.join(os.path.dirname(_HERE), "iggt_official_b200", "state_layout.json")
 
 
 def load_manifest():

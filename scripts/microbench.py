@@ -29,10 +29,15 @@ def timeit(fn, reps=10, warmup=3, flush=None):
 
 
 def main():
+    """--views V: rows of V views (default 8 = one GPU at C2; 1 = one rank of eight)."""
     dt = torch.float16
     dev = "cuda"
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    M = 8 * 1374
+    V = int(sys.argv[sys.argv.index("--views") + 1]) if "--views" in sys.argv else 8
+    noflush = "--noflush" in sys.argv          # inside a step the residual stream / weights of a layer are L2-warm
+    if noflush:
+        flush = None
+    M = V * 1374
     res = {}
     a = torch.randn(M, 1024, device=dev).to(dt)
     a4 = torch.randn(M, 4096, device=dev).to(dt)
@@ -65,7 +70,7 @@ def main():
     # attention: frame (8 seq x 1374) and global (1 seq x 10992)
     qkv = torch.randn(M, 3072, device=dev).to(dt)
     out = torch.empty(M, 1024, device=dev, dtype=dt)
-    for name, ns, L in [("attn_frame", 8, 1374), ("attn_global", 1, M)]:
+    for name, ns, L in [("attn_frame", V, 1374), ("attn_global", 1, M)]:
         fn = lambda: ops.attention(qkv[:, :1024], qkv[:, 1024:2048], qkv[:, 2048:], ns, L, L, 16, out=out)
         ms = timeit(fn, flush=flush)
         fl = 4.0 * ns * L * L * 1024
@@ -80,11 +85,11 @@ def main():
     ms = timeit(lambda: ops.layernorm(x, w, b, 1e-5, y), flush=flush)
     res["layernorm"] = {"ms": ms, "gbs": M * 1024 * 6 / ms / 1e6}
     # conv 3x3 256->256 at 148^2 x 8 views
-    xc = torch.randn(8, 148, 148, 256, device=dev).to(dt)
+    xc = torch.randn(V, 148, 148, 256, device=dev).to(dt)
     wc = (torch.randn(256, 9 * 256, device=dev) / 48).to(dt)
-    oc = torch.empty(8, 148, 148, 256, device=dev, dtype=dt)
+    oc = torch.empty(V, 148, 148, 256, device=dev, dtype=dt)
     ms = timeit(lambda: ops.conv_nhwc(xc, wc, None, act=2, out=oc), flush=flush)
-    res["conv3x3_148"] = {"ms": ms, "tflops": 2.0 * 8 * 148 * 148 * 256 * 2304 / ms / 1e9}
+    res["conv3x3_148"] = {"ms": ms, "tflops": 2.0 * V * 148 * 148 * 256 * 2304 / ms / 1e9}
     # camera-head skinny GEMM (M = 8 camera tokens): weight streaming
     xs = torch.randn(8, 2048, device=dev)
     ws = (torch.randn(6144, 2048, device=dev) / 45).to(dt)

@@ -9,10 +9,13 @@ fp32 summation order flips 16-bit roundings, and ~1e-4 per block accumulates to 
   gap_amp  = oracle(amp) vs oracle(fp32)                      (autocast vs fp32)
   gap_tf32 = oracle(amp, cuDNN TF32 convs) vs oracle(amp)     (PyTorch's GPU default for the reference's fp32 heads)
 Asserted, relative L2 against oracle(amp):
-  fp16 trunk: depth, depth_conf, world_points_conf <= 1e-3 (north_star's figure);
-              pose_enc <= max(1e-3, 1.5 gap_amp);  world_points, part_feat (amplified by sign*expm1 / 30+ conv layers,
-              10-bit-mantissa operands like TF32) <= 1.6 max(gap_amp, gap_tf32);
-  bf16 trunk: every key <= 1.5 (1.6) x its gap (the heads still run fp16 operands, iggt/models/vggt.py:189)."""
+  fp16 trunk: depth, depth_conf, world_points_conf, pose_enc <= 1e-3 (north_star's figure);
+              world_points, part_feat (amplified by sign*expm1 / 30+ conv layers; operands carry a 10-bit mantissa
+              like the reference's own TF32 convolutions) <= 1.3 max(gap_amp, gap_tf32);
+  bf16 trunk: every key <= 1.2 x max(gap_amp, gap_tf32) (the heads still run fp16 operands, iggt/models/vggt.py:189).
+Measured on B200 (profiles/r02_parity_fullsize.json, stress weights): C2 fp16 depth 6.6e-4, conf 3.1e-4 / 4.8e-4,
+pose 5.1e-4, world_points 2.19e-3 = 1.09 x gap_tf32 (PyTorch's own TF32 heads sit 2.02e-3 from its fp32 heads on the
+same tokens); IGGT 8 x 532^2 part_feat 1.67e-3 = 1.18 x gap_tf32; bf16 trunks 0.3 - 0.7 x their gaps."""
 import pytest
 import torch
 
@@ -25,18 +28,15 @@ CASES = [
     ("iggt", 1, 3, 336, 504, torch.float16),       # C1 shape
     ("iggt", 1, 3, 336, 504, torch.bfloat16),
 ]
-TIGHT = ("depth", "depth_conf", "world_points_conf")
 AMPLIFIED = ("world_points", "part_feat")
 
 
 def bound(row, key, dtype):
     e = row[key]
     gap = max(e["gap_amp_l2"], e.get("gap_tf32_l2", 0.0))
-    if key in AMPLIFIED:
-        return 1.6 * gap
     if dtype == torch.float16:
-        return 1e-3 if key in TIGHT else max(1e-3, 1.5 * e["gap_amp_l2"])
-    return 1.5 * max(gap, 1e-3 / 1.5)
+        return 1.3 * gap if key in AMPLIFIED else 1e-3
+    return 1.2 * max(gap, 1e-3 / 1.2)
 
 
 @pytest.fixture(scope="module")

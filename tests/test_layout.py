@@ -11,9 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_layout_file_matches_reference_manifest():
-    a = json.load(open(os.path.join(ROOT, "oracle", "state_manifest.json")))
+    """The product's schema file against the digest of the list extracted from the unmodified reference
+    (oracle/make_manifest.py -> oracle/state_manifest.sha256.json)."""
+    import hashlib
+    rec = json.load(open(os.path.join(ROOT, "oracle", "state_manifest.sha256.json")))
     b = json.load(open(os.path.join(ROOT, "iggt_official_b200", "state_layout.json")))
-    assert a == b and len(a) == 2053
+    assert len(b) == rec["entries"] == 2053
+    assert hashlib.sha256(json.dumps(b, separators=(",", ":")).encode()).hexdigest() == rec["sha256_canonical_json"]
 
 
 @pytest.fixture(scope="module")
