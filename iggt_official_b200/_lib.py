@@ -51,6 +51,8 @@ SIGNATURES = {
     "iggt_skinny_gemm": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                          c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "iggt_small_attention": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "iggt_camera_head_workspace": [c_int],
+    "iggt_camera_head": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
     "iggt_layernorm16": [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p],
     "iggt_col2im_k4s2p1": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "iggt_ocab_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -83,6 +85,18 @@ SIGNATURES = {
 }
 
 
+class CameraBlock(ctypes.Structure):
+    """iggt_camera_block (include/iggt_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1", "n2w", "n2b", "fc1_w",
+                                        "fc1_b", "fc2_w", "fc2_b", "ls2")]
+
+
+class CameraWeights(ctypes.Structure):
+    """iggt_camera_weights (include/iggt_b200.h)"""
+    _fields_ = ([(n, c_void_p) for n in ("emb_w", "emb_b", "mod_w", "mod_b")] + [("blk", CameraBlock * 4)] +
+                [(n, c_void_p) for n in ("tok_w", "tok_b", "trk_w", "trk_b", "pb1_w", "pb1_b", "pb2_w", "pb2_b", "empty")])
+
+
 def build(verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", CSRC_DIR, "-j", str(min(16, os.cpu_count() or 4))]
@@ -109,6 +123,7 @@ def load():
         fn.restype = c_int
     lib.iggt_version.restype = ctypes.c_char_p
     lib.iggt_version.argtypes = []
+    lib.iggt_camera_head_workspace.restype = c_int64
     _lib = lib
     return lib
 

@@ -595,8 +595,10 @@ int launch_attention3(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtens
 using namespace iggt;
 
 namespace {
-// Cost (in kv-tile steps of one CTA) of running the launch with `splits` kv ranges on `sms` CTAs: rounds x (tiles per
-// split + a fixed per-item overhead: Q load, first-tile max, O read-out) + the merge pass over the fp32 workspace.
+// Cost (in kv-tile steps of one CTA, ~1.4 us) of running the launch with `splits` kv ranges on `sms` CTAs: rounds x (tiles
+// per split + a fixed per-item overhead: Q load, pipeline fill, first-tile max, O read-out) + the merge pass over the fp32
+// workspace.  Constants fitted to the B200 sweep profiles/r02b_attn_sweep.json (1 of 8 / 4 / 2 views against 8 views of
+// keys, 1..5 splits): 7 steps per item, 10 steps + traffic for the merge launch; predictions within 6 % of measured.
 double attn3_cost(int num_seq, int Lq, int Lk, int H, int splits, int sms) {
   const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ, n_kv = (Lk + A3_BK - 1) / A3_BK;
   const int tps = (n_kv + splits - 1) / splits, se = (n_kv + tps - 1) / tps;
@@ -610,10 +612,10 @@ double attn3_cost(int num_seq, int Lq, int Lk, int H, int splits, int sms) {
     const double by_full = static_cast<double>(static_cast<long>(full / sms + 0.999999));
     rounds = by_weight > by_full ? by_weight : by_full;
   }
-  double cost = rounds * (tps + 2.0);
+  double cost = rounds * (tps + 7.0);
   if (se > 1) {
     const double ws_bytes = 2.0 * se * num_seq * Lq * H * A3_D * 4;     // written + read back
-    cost += 2.0 + ws_bytes / 4.0e12 / 1.36e-6;                           // ~4 TB/s through L2, 1.36 us per kv-tile step
+    cost += 10.0 + ws_bytes / 4.0e12 / 1.4e-6;                           // ~4 TB/s through L2, 1.4 us per kv-tile step
   }
   return cost;
 }
@@ -717,17 +719,17 @@ int attention_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int stag = [] { const char* e = getenv("IGGT_ATTN_STAG"); return e ? atoi(e) : 2; }();
   p.stagger_at = stag < 0 ? 0 : (stag > 4 ? 4 : stag);
-  // IGGT_ATTN_EMU = how many of every 8 probability pairs take the FMA-pipe exp2 (0..4); IGGT_ATTN_PT=0 keeps P in
-  // shared memory (the pre-TMEM variant, MUFU only)
-  static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); int v = e ? atoi(e) : A3_DEFAULT_EMU8; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
+  // IGGT_ATTN_EMU=1: 2 of every 8 probability pairs take the packed FMA-pipe exp2 (ex2_emulated2).  Measured on B200
+  // (profiles/r02b_attn_sweep.json: 0..4 of 8 pairs -> global 638 / 675 / 654 / 656 / 706 us, frame 124 / 128 / 124 /
+  // 124 / 132 us): no variant beats the MUFU-only kernel - halving the MUFU work makes the kernel SLOWER, so the softmax
+  // warps are bound by their dependency chain (S load -> max -> bar.red -> exp -> P store), not by MUFU throughput.
+  // Kept as an off-by-default experiment.  IGGT_ATTN_PT=0 keeps P in shared memory (the pre-TMEM variant).
+  static const int emu = [] { const char* e = getenv("IGGT_ATTN_EMU"); int v = e ? atoi(e) : A3_DEFAULT_EMU8; return v > 0 ? 2 : 0; }();
   static const int pt = [] { const char* e = getenv("IGGT_ATTN_PT"); return e ? atoi(e) : 1; }();
   int st;
   if (!pt) st = dtype ? launch_attention3<true, 0, false>(tQ, tK, tV, p, s) : launch_attention3<false, 0, false>(tQ, tK, tV, p, s);
   else switch (emu) {
-    case 1: st = dtype ? launch_attention3<true, 1, true>(tQ, tK, tV, p, s) : launch_attention3<false, 1, true>(tQ, tK, tV, p, s); break;
     case 2: st = dtype ? launch_attention3<true, 2, true>(tQ, tK, tV, p, s) : launch_attention3<false, 2, true>(tQ, tK, tV, p, s); break;
-    case 3: st = dtype ? launch_attention3<true, 3, true>(tQ, tK, tV, p, s) : launch_attention3<false, 3, true>(tQ, tK, tV, p, s); break;
-    case 4: st = dtype ? launch_attention3<true, 4, true>(tQ, tK, tV, p, s) : launch_attention3<false, 4, true>(tQ, tK, tV, p, s); break;
     default: st = dtype ? launch_attention3<true, 0, true>(tQ, tK, tV, p, s) : launch_attention3<false, 0, true>(tQ, tK, tV, p, s);
   }
   if (st != 0 || p.kv_splits == 1) return st;

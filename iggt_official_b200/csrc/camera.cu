@@ -1,0 +1,462 @@
+// The whole camera head (iggt/heads/camera_head.py:83-154 + head_act.py:12-35) as ONE persistent kernel.
+//
+// M = B*S <= 16 camera tokens against 216 M parameters, four refinement iterations: every Linear is a weight stream
+// (1.7 GB of 16-bit weights per forward, 0.27 ms at HBM speed) with a few MFLOP of work, but as separate launches it is
+// ~180 dependent kernels of 5-20 us each (LayerNorm / skinny GEMM / tiny attention / AdaLN glue), i.e. launch- and
+// latency-bound: 2.0 ms of the 54 ms C2 step on one GPU and 12 % of the step on each of 8 view-sharded ranks, where the
+// head is replicated.  Here the ~27 phases of an iteration run inside one grid of <= 128 CTAs with a device-wide barrier
+// between phases:
+//   * warp 8 is a TMA producer that walks the same phase program AHEAD of the consumers: weight tiles
+//     ({256 k, 16 columns}, 8 KB) of the next phases stream into an 8-stage ring while the consumers are still in the
+//     barrier of the current one - weights do not depend on activations - so HBM stays busy across phase boundaries;
+//   * activations are tiny and live in L2: after each barrier the 8 consumer warps pull the phase's input rows
+//     ([M, <= 2048] fp32) into shared memory, applying the LayerNorm that precedes the Linear on the way (statistics over
+//     the row, two-pass in registers), stored k-major / row-minor so that a thread's fma pairs are packed (FFMA2);
+//   * consumer warp w owns 2 of the tile's 16 columns for all M rows; lanes split k; one butterfly reduction per tile;
+//     bias, exact-erf GELU / SiLU, LayerScale, residual and the pose accumulation + activation ride in the epilogue;
+//   * the S x S attention (16 heads x 128) is a phase of its own: one warp per (row, head).
+// fp32 activations and accumulation, 16-bit weights - the arithmetic of iggt_skinny_gemm / iggt_small_attention, which
+// this kernel replaces for M <= 16 (larger B*S keep the per-layer launches).
+#include <stdlib.h>
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include "launch.cuh"
+#include "../../include/iggt_b200.h"
+
+namespace iggt {
+
+constexpr int CAM_DIM = 2048, CAM_HEADS = 16, CAM_HD = 128;
+constexpr int CAM_THREADS = 288;              // 8 consumer warps + 1 producer warp
+constexpr int CAM_COLS = 16;                  // output columns per tile
+constexpr int CAM_KC = 256;                   // k per weight stage
+constexpr int CAM_STAGES = 8;
+constexpr int CAM_W_BYTES = CAM_COLS * CAM_KC * 2;       // 8 KB
+constexpr int CAM_X_FLOATS = 16384;           // activation buffer: [k][Mpad] fp32, 64 KB
+constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + 256;
+constexpr int CAM_MAX_PHASES = 32, CAM_MAX_MAPS = 24;
+
+enum CamPhaseType : int { PH_GEMM = 0, PH_ATTN = 1, PH_MODULATE = 2, PH_LNROWS = 3 };
+enum CamFlags : int { CF_EMBED_IN = 1, CF_POSE_OUT = 2, CF_ONCE = 4 };     // CF_ONCE: only before the first iteration
+
+struct CamPhase {
+  int type, tm, N, K;
+  const float* x; long ldx;
+  int ln;                      // 0 none, 1 LayerNorm (ln_w, ln_b), 2 LayerNorm without affine
+  float ln_eps;
+  const float* ln_w; const float* ln_b;
+  const float* bias; const float* gamma; const float* resid; long ldr;
+  float* out; long ldo;
+  int act;                     // 0 none, 1 exact GELU, 4 SiLU
+  int flags;
+  const float* x2;             // CF_EMBED_IN: the empty pose token [16]; PH_MODULATE: ptn
+  const float* x3;             // PH_MODULATE: pt
+  float* out2;                 // CF_POSE_OUT: activated poses [iters][M][9]
+};
+
+struct CamProgram {
+  CUtensorMap maps[CAM_MAX_MAPS];
+  CamPhase ph[CAM_MAX_PHASES];
+  int n_phases, iters, M, Mpad, B, S;
+  unsigned* barrier;           // zeroed before the launch
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// device-wide barrier of the consumer warps (256 threads per CTA; the producer warp never joins)
+__device__ __forceinline__ void cam_grid_sync(unsigned* counter, unsigned& target) {
+  named_bar_sync(1, 256);
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < target) { __nanosleep(20); }
+    __threadfence();
+  }
+  named_bar_sync(1, 256);
+}
+
+template <bool BF16>
+__device__ __forceinline__ void cam_unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (BF16) {
+      f[2 * j] = __uint_as_float(w[j] << 16);
+      f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    } else {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      f[2 * j] = __low2float(h);
+      f[2 * j + 1] = __high2float(h);
+    }
+  }
+}
+
+// Position of activation k inside the staged buffer: a consumer lane owns the 8 consecutive k of its uint4 of weights
+// (k = 8 * lane + j inside a 256-wide stage); storing them at (j * 32 + lane) makes the lanes' 32-byte row groups
+// consecutive in shared memory for every j (conflict-free LDS.128) instead of 256 bytes apart (8-way conflicts).
+__device__ __forceinline__ int cam_perm(int k) { return (k & ~255) | ((k & 7) << 5) | ((k >> 3) & 31); }
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// MP = padded row count (8 or 16): xs is [k][MP]
+template <bool BF16, int MP>
+__global__ void __launch_bounds__(CAM_THREADS, 1)
+camera_head_kernel(const __grid_constant__ CamProgram prog) {
+  extern __shared__ __align__(128) uint8_t cam_smem[];
+  uint8_t* sW = cam_smem;
+  float* xs = reinterpret_cast<float*>(cam_smem + CAM_STAGES * CAM_W_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4);
+  uint64_t* empty = full + CAM_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int M = prog.M;
+  constexpr int KX = CAM_X_FLOATS / MP;          // k extent of the activation buffer (2048 / 1024)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CAM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer: runs ahead of the barriers
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int it = 0; it < prog.iters; ++it)
+        for (int p = 0; p < prog.n_phases; ++p) {
+          const CamPhase& P = prog.ph[p];
+          if (P.type != PH_GEMM || ((P.flags & CF_ONCE) && it > 0)) continue;
+          const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
+          const int nkb = (P.K + CAM_KC - 1) / CAM_KC;
+          for (int t = cta; t < tiles; t += G)
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(&empty[st], ph ^ 1);
+              mbar_expect_tx(&full[st], CAM_W_BYTES);
+              tma_load_2d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], kb * CAM_KC, t * CAM_COLS);
+              if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers (8 warps)
+  const int tid = threadIdx.x;                   // 0..255
+  unsigned target = 0;
+  int st = 0; uint32_t ph = 0;
+  for (int it = 0; it < prog.iters; ++it)
+    for (int p = 0; p < prog.n_phases; ++p) {
+      const CamPhase& P = prog.ph[p];
+      if ((P.flags & CF_ONCE) && it > 0) continue;
+      if (P.type == PH_GEMM) {
+        const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
+        const int nchunks = (P.K + KX - 1) / KX;                         // activation chunks of KX
+        const bool embed0 = (P.flags & CF_EMBED_IN) && it == 0;
+        for (int t = cta; t < tiles; t += G) {
+          float2 acc[2][MP / 2];
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int m = 0; m < MP / 2; ++m) acc[c][m] = make_float2(0.f, 0.f);
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int k0 = ch * KX;
+            const int kn = min(KX, ((P.K - k0 + CAM_KC - 1) / CAM_KC) * CAM_KC);   // staged k extent (multiple of 256)
+            if (t == cta || nchunks > 1) {
+              // ---- stage the activations [M, kn] (k-major, row-minor), LayerNorm applied on the way
+              named_bar_sync(2, 256);                                     // previous readers of xs are done
+              for (int m = warp; m < MP; m += 8) {
+                if (m >= M) {
+                  for (int k = lane; k < kn; k += 32) xs[k * MP + m] = 0.f;          // (a permutation of [0, kn): any order)
+                  continue;
+                }
+                const float* row = embed0 ? P.x2 : P.x + m * P.ldx;
+                if (P.ln) {                                               // K == 2048 == KX or 2 * KX
+                  float v[CAM_DIM / 32];
+                  float s = 0.f;
+#pragma unroll
+                  for (int i = 0; i < CAM_DIM / 128; ++i) {
+                    const float4 a = *reinterpret_cast<const float4*>(row + (lane + 32 * i) * 4);
+                    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                    s += (a.x + a.y) + (a.z + a.w);
+                  }
+                  const float mean = warp_sum_f(s) * (1.0f / CAM_DIM);
+                  float q = 0.f;
+#pragma unroll
+                  for (int i = 0; i < CAM_DIM / 32; ++i) { const float d = v[i] - mean; q += d * d; }
+                  const float rstd = rsqrtf(warp_sum_f(q) * (1.0f / CAM_DIM) + P.ln_eps);
+#pragma unroll
+                  for (int i = 0; i < CAM_DIM / 128; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const int k = (lane + 32 * i) * 4 + j;
+                      float y = (v[4 * i + j] - mean) * rstd;
+                      if (P.ln == 1) y = y * P.ln_w[k] + P.ln_b[k];
+                      if (k >= k0 && k < k0 + kn) xs[cam_perm(k - k0) * MP + m] = y;
+                    }
+                } else {
+                  for (int k = lane; k < kn; k += 32) xs[cam_perm(k) * MP + m] = (k0 + k < P.K) ? row[k0 + k] : 0.f;
+                }
+              }
+              named_bar_sync(2, 256);
+            }
+            // ---- weight stages of this chunk
+            for (int kb = 0; kb < kn / CAM_KC; ++kb) {
+              mbar_wait(&full[st], ph);
+              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (warp * 2) * CAM_KC + lane * 8;
+              const float* xk = xs + (kb * CAM_KC + lane) * MP;            // cam_perm: element j of this lane at + j * 32 rows
+              float w0[8], w1[8];
+              cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w), w0);
+              cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + CAM_KC), w1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 wa = make_float2(w0[j], w0[j]), wb = make_float2(w1[j], w1[j]);
+#pragma unroll
+                for (int m4 = 0; m4 < MP / 4; ++m4) {
+                  const float4 xv = *reinterpret_cast<const float4*>(xk + j * 32 * MP + m4 * 4);
+                  acc[0][2 * m4] = ffma2(make_float2(xv.x, xv.y), wa, acc[0][2 * m4]);
+                  acc[0][2 * m4 + 1] = ffma2(make_float2(xv.z, xv.w), wa, acc[0][2 * m4 + 1]);
+                  acc[1][2 * m4] = ffma2(make_float2(xv.x, xv.y), wb, acc[1][2 * m4]);
+                  acc[1][2 * m4 + 1] = ffma2(make_float2(xv.z, xv.w), wb, acc[1][2 * m4 + 1]);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[st]);
+              if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
+            }
+          }
+          // ---- reduce over the lanes' k slices; lane (c * MP + m) keeps column c, row m
+          float mine = 0.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int m = 0; m < MP; ++m) {
+              float v = (m & 1) ? acc[c][m >> 1].y : acc[c][m >> 1].x;
+              v = warp_sum_f(v);
+              if (lane == c * MP + m) mine = v;
+            }
+          if (lane < 2 * MP) {
+            const int c = lane / MP, m = lane % MP;
+            const int n = t * CAM_COLS + warp * 2 + c;
+            if (n < P.N && m < M) {
+              float v = mine + (P.bias ? P.bias[n] : 0.f);
+              if (P.act == 1) v = gelu_erf(v);
+              else if (P.act == 4) v = v / (1.0f + expf(-v));
+              if (P.gamma) v *= P.gamma[n];
+              if (P.flags & CF_POSE_OUT) {
+                if (it > 0) v += P.out[m * P.ldo + n];                    // pred += delta
+                P.out2[(static_cast<long>(it) * M + m) * 9 + n] = n >= 7 ? fmaxf(v, 0.f) : v;   // activate_pose
+              } else if (P.resid) {
+                v += P.resid[m * P.ldr + n];
+              }
+              P.out[m * P.ldo + n] = v;
+            }
+          }
+        }
+      } else if (P.type == PH_ATTN) {
+        // one warp per (row, head): q . k_j over the S tokens of the row's scene, softmax, p . v
+        const int items = M * CAM_HEADS;
+        for (int i = cta * 8 + warp; i < items; i += G * 8) {
+          const int m = i / CAM_HEADS, h = i % CAM_HEADS;
+          const int b = m / prog.S;
+          const float* qkv = P.x;
+          const float4 q = *reinterpret_cast<const float4*>(qkv + m * P.ldx + h * CAM_HD + lane * 4);
+          float s[16];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < prog.S) {
+              const float4 k = *reinterpret_cast<const float4*>(qkv + (b * prog.S + j) * P.ldx + CAM_DIM + h * CAM_HD + lane * 4);
+              s[j] = warp_sum_f(q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w) * 0.08838834764831845f;   // 128^-0.5
+              mx = fmaxf(mx, s[j]);
+            }
+          }
+          float sum = 0.f;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < prog.S) {
+              const float e = expf(s[j] - mx);
+              sum += e;
+              const float4 v = *reinterpret_cast<const float4*>(qkv + (b * prog.S + j) * P.ldx + 2 * CAM_DIM + h * CAM_HD + lane * 4);
+              o.x = fmaf(e, v.x, o.x); o.y = fmaf(e, v.y, o.y); o.z = fmaf(e, v.z, o.z); o.w = fmaf(e, v.w, o.w);
+            }
+          }
+          const float inv = 1.0f / sum;
+          *reinterpret_cast<float4*>(P.out + m * P.ldo + h * CAM_HD + lane * 4) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+        }
+      } else if (P.type == PH_MODULATE) {
+        // x = gate * (ptn * (1 + scale) + shift) + pt   (camera_head.py:119-121, modulate :157-161); mod = [shift|scale|gate]
+        for (int i = cta * 256 + tid; i < M * CAM_DIM; i += G * 256) {
+          const int m = i / CAM_DIM, k = i % CAM_DIM;
+          const float* mod = P.x + m * P.ldx;
+          P.out[m * P.ldo + k] = mod[2 * CAM_DIM + k] * (P.x2[i] * (1.0f + mod[CAM_DIM + k]) + mod[k]) + P.x3[i];
+        }
+      } else {   // PH_LNROWS: out[m] = LayerNorm(x[m]) over 2048, one warp per row
+        for (int m = cta * 8 + warp; m < M; m += G * 8) {
+          const float* row = P.x + m * P.ldx;
+          float v[CAM_DIM / 32];
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < CAM_DIM / 128; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(row + (lane + 32 * i) * 4);
+            v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            s += (a.x + a.y) + (a.z + a.w);
+          }
+          const float mean = warp_sum_f(s) * (1.0f / CAM_DIM);
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < CAM_DIM / 32; ++i) { const float d = v[i] - mean; q += d * d; }
+          const float rstd = rsqrtf(warp_sum_f(q) * (1.0f / CAM_DIM) + P.ln_eps);
+#pragma unroll
+          for (int i = 0; i < CAM_DIM / 128; ++i) {
+            const int k = (lane + 32 * i) * 4;
+            float4 y = make_float4((v[4 * i] - mean) * rstd, (v[4 * i + 1] - mean) * rstd, (v[4 * i + 2] - mean) * rstd,
+                                   (v[4 * i + 3] - mean) * rstd);
+            if (P.ln == 1) {
+              const float4 ww = *reinterpret_cast<const float4*>(P.ln_w + k), bb = *reinterpret_cast<const float4*>(P.ln_b + k);
+              y.x = y.x * ww.x + bb.x; y.y = y.y * ww.y + bb.y; y.z = y.z * ww.z + bb.z; y.w = y.w * ww.w + bb.w;
+            }
+            *reinterpret_cast<float4*>(P.out + m * P.ldo + k) = y;
+          }
+        }
+      }
+      cam_grid_sync(prog.barrier, target);
+    }
+}
+
+}  // namespace iggt
+
+using namespace iggt;
+
+namespace {
+struct CamWs {          // workspace layout (floats), M rows each
+  float *pt, *ptn, *e, *mod, *x, *qkv, *o, *f, *hdn, *pred;
+  unsigned* barrier;
+};
+int64_t cam_ws_floats(int M) { return static_cast<int64_t>(M) * (5 * CAM_DIM + 2 * 3 * CAM_DIM + 4 * CAM_DIM + 1024 + 16); }
+}  // namespace
+
+extern "C" int64_t iggt_camera_head_workspace(int M) {
+  if (M <= 0) return -1;
+  return cam_ws_floats(M) * 4 + 256;
+}
+
+extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* tokens, int64_t ld_tokens, float* out,
+                                void* workspace, int64_t ws_bytes, int B, int S, int iters, int dtype,
+                                iggt_stream_t stream) {
+  if (!w || !tokens || !out || !workspace || B <= 0 || S <= 0 || iters <= 0) return -1;
+  const int M = B * S;
+  if (M > 16 || S > 16) return -7;                      // larger batches: the per-layer launches (iggt_skinny_gemm ...)
+  if (dtype != 0 && dtype != 1) return -3;
+  if (ws_bytes < iggt_camera_head_workspace(M) || (reinterpret_cast<uintptr_t>(workspace) & 15) || (ld_tokens % 4)) return -6;
+  cudaStream_t s = (cudaStream_t)stream;
+  CamWs ws;
+  float* p = reinterpret_cast<float*>(workspace);
+  ws.pt = p; p += M * CAM_DIM;
+  ws.ptn = p; p += M * CAM_DIM;
+  ws.e = p; p += M * CAM_DIM;
+  ws.x = p; p += M * CAM_DIM;
+  ws.o = p; p += M * CAM_DIM;
+  ws.mod = p; p += M * 3 * CAM_DIM;
+  ws.qkv = p; p += M * 3 * CAM_DIM;
+  ws.f = p; p += M * 4 * CAM_DIM;
+  ws.hdn = p; p += M * 1024;
+  ws.pred = p; p += M * 16;
+  ws.barrier = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(p) + 127) & ~static_cast<uintptr_t>(127));
+  cudaError_t e = cudaMemsetAsync(ws.barrier, 0, 4, s);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(ws.pred, 0, M * 16 * 4, s);       // columns 9..15 of `pred` are the zero padding of embed_pose's K
+  if (e != cudaSuccess) return (int)e;
+
+  CamProgram prog{};
+  prog.iters = iters; prog.M = M; prog.Mpad = M <= 8 ? 8 : 16; prog.B = B; prog.S = S; prog.barrier = ws.barrier;
+  const TmDtype dt = dtype ? TM_BF16 : TM_F16;
+  int nmaps = 0;
+  auto add_map = [&](const void* W, int N, int K) -> int {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {(uint32_t)CAM_KC, (uint32_t)CAM_COLS};
+    if (nmaps >= CAM_MAX_MAPS || make_tmap(&prog.maps[nmaps], dt, 2, W, dims, str, box, false)) return -1;
+    return nmaps++;
+  };
+  int np = 0;
+  bool bad = false;
+  auto gemm = [&](const void* W, int N, int K, const float* x, long ldx, const float* bias, float* o, long ldo, int act) -> CamPhase& {
+    CamPhase& P = prog.ph[np++];
+    P = CamPhase{};
+    P.type = PH_GEMM; P.N = N; P.K = K; P.x = x; P.ldx = ldx; P.bias = bias; P.out = o; P.ldo = ldo; P.act = act;
+    P.tm = add_map(W, N, K);
+    if (P.tm < 0) bad = true;
+    return P;
+  };
+  auto ln = [](CamPhase& P, const float* lw, const float* lb, float eps) { P.ln = lw ? 1 : 2; P.ln_w = lw; P.ln_b = lb; P.ln_eps = eps; };
+  {   // pose_tokens = token_norm(tokens[:, :, 0]); adaln_norm(pose_tokens)  (camera_head.py:99-100, :117)
+    CamPhase& P0 = prog.ph[np++]; P0 = CamPhase{};
+    P0.type = PH_LNROWS; P0.x = tokens; P0.ldx = ld_tokens; P0.out = ws.pt; P0.ldo = CAM_DIM; P0.flags = CF_ONCE;
+    ln(P0, w->tok_w, w->tok_b, 1e-5f);
+    CamPhase& P1 = prog.ph[np++]; P1 = CamPhase{};
+    P1.type = PH_LNROWS; P1.x = ws.pt; P1.ldx = CAM_DIM; P1.out = ws.ptn; P1.ldo = CAM_DIM; P1.flags = CF_ONCE;
+    ln(P1, nullptr, nullptr, 1e-6f);
+  }
+  {   // module_input = embed_pose(prev or empty); shift / scale / gate = Linear(SiLU(.))  (camera_head.py:105-115)
+    CamPhase& E = gemm(w->emb_w, CAM_DIM, 16, ws.pred, 16, w->emb_b, ws.e, CAM_DIM, 4);
+    E.flags = CF_EMBED_IN; E.x2 = w->empty;
+    gemm(w->mod_w, 3 * CAM_DIM, CAM_DIM, ws.e, CAM_DIM, w->mod_b, ws.mod, 3 * CAM_DIM, 0);
+    CamPhase& Mo = prog.ph[np++]; Mo = CamPhase{};
+    Mo.type = PH_MODULATE; Mo.x = ws.mod; Mo.ldx = 3 * CAM_DIM; Mo.x2 = ws.ptn; Mo.x3 = ws.pt; Mo.out = ws.x; Mo.ldo = CAM_DIM;
+  }
+  for (int b = 0; b < 4; ++b) {   // trunk blocks (layers/block.py:105-106, LayerScale init 0.01)
+    const auto& k = w->blk[b];
+    CamPhase& Q = gemm(k.qkv_w, 3 * CAM_DIM, CAM_DIM, ws.x, CAM_DIM, k.qkv_b, ws.qkv, 3 * CAM_DIM, 0);
+    ln(Q, k.n1w, k.n1b, 1e-5f);
+    CamPhase& A = prog.ph[np++]; A = CamPhase{};
+    A.type = PH_ATTN; A.x = ws.qkv; A.ldx = 3 * CAM_DIM; A.out = ws.o; A.ldo = CAM_DIM;
+    CamPhase& Pr = gemm(k.proj_w, CAM_DIM, CAM_DIM, ws.o, CAM_DIM, k.proj_b, ws.x, CAM_DIM, 0);
+    Pr.gamma = k.ls1; Pr.resid = ws.x; Pr.ldr = CAM_DIM;
+    CamPhase& F1 = gemm(k.fc1_w, 4 * CAM_DIM, CAM_DIM, ws.x, CAM_DIM, k.fc1_b, ws.f, 4 * CAM_DIM, 1);
+    ln(F1, k.n2w, k.n2b, 1e-5f);
+    CamPhase& F2 = gemm(k.fc2_w, CAM_DIM, 4 * CAM_DIM, ws.f, 4 * CAM_DIM, k.fc2_b, ws.x, CAM_DIM, 0);
+    F2.gamma = k.ls2; F2.resid = ws.x; F2.ldr = CAM_DIM;
+  }
+  {   // pose_branch(trunk_norm(.)) and the accumulation / activation  (camera_head.py:124-139)
+    CamPhase& B1 = gemm(w->pb1_w, 1024, CAM_DIM, ws.x, CAM_DIM, w->pb1_b, ws.hdn, 1024, 1);
+    ln(B1, w->trk_w, w->trk_b, 1e-5f);
+    CamPhase& B2 = gemm(w->pb2_w, 9, 1024, ws.hdn, 1024, w->pb2_b, ws.pred, 16, 0);
+    B2.flags = CF_POSE_OUT; B2.out2 = out;
+  }
+  if (bad || np > CAM_MAX_PHASES) return -4;
+  prog.n_phases = np;
+
+  const int sms = device_sm_count();
+  const int grid = sms >= 128 ? 128 : sms;           // 128 | every tile count of the head (128 / 384 / 512): no ragged wave
+  void (*kern)(const CamProgram) = nullptr;
+  if (prog.Mpad == 8) kern = dtype ? camera_head_kernel<true, 8> : camera_head_kernel<false, 8>;
+  else kern = dtype ? camera_head_kernel<true, 16> : camera_head_kernel<false, 16>;
+  static DeviceOnce once;
+  if (once.first()) {
+    cudaFuncSetAttribute(camera_head_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
+    cudaFuncSetAttribute(camera_head_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
+    cudaFuncSetAttribute(camera_head_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
+    cudaFuncSetAttribute(camera_head_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAM_SMEM);
+  }
+  // every CTA must be resident for the device-wide barrier: a cooperative launch guarantees it (or fails loudly)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CAM_THREADS);
+  cfg.dynamicSmemBytes = CAM_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, prog);
+}

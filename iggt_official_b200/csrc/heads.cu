@@ -36,43 +36,64 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // + optional pos-embed: channels [0,C/2) get tabx[x][c], [C/2,C) get taby[y][c-C/2]
 // (iggt/heads/dpt_head.py:274-284, iggt/heads/utils.py:11-108; tables are built on the host in float64).
 template <bool BF16>
+__device__ __forceinline__ float2 cvt16x2(uint32_t u) {
+  if constexpr (BF16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+  else return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// One CTA per output row (n, oy): the vertical taps / weights are row constants, a thread walks (ox, 8-channel group)
+// items of the row.  The four-tap blend runs on packed fp32 pairs (FMUL2 / FFMA2, same IEEE results as scalar code):
+// the first version of this kernel was issue-bound (ncu: 71 % issue slots, 1.8 TB/s; profiles/r02a_ncu_all_kernels.csv)
+// on 64-bit index arithmetic and scalar blends.
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 upsample_bilinear_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int NB, int h, int w,
                          int H, int W, int C, const float* __restrict__ tabx, const float* __restrict__ taby) {
   const int cv = C / 8;
-  const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
+  const int row = blockIdx.x;                                   // n * H + oy
+  const int n = row / H, oy = row - n * H;
   const float sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
   const float sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
-  const uint32_t per_img = static_cast<uint32_t>(H) * W * cv;     // < 2^31 for every head resolution
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    // 32-bit index arithmetic (64-bit div/mod is emulated and dominated this kernel)
-    const int n = static_cast<int>(i / per_img);
-    uint32_t r = static_cast<uint32_t>(i - static_cast<int64_t>(n) * per_img);
-    const int c8 = static_cast<int>(r % static_cast<uint32_t>(cv)); r /= static_cast<uint32_t>(cv);
-    const int ox = static_cast<int>(r % static_cast<uint32_t>(W));
-    const int oy = static_cast<int>(r / static_cast<uint32_t>(W));
-    const float fy = sy * oy, fx = sx * ox;
-    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = fy - y0, lx = fx - x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const uint16_t* base = x + static_cast<int64_t>(n) * h * w * C + c8 * 8;
-    float a[8], b[8], c[8], d[8], o[8];
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * w + x0) * C)), a);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * w + x1) * C)), b);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * w + x0) * C)), c);
-    unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * w + x1) * C)), d);
+  const float fy = sy * oy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = min(y0 + 1, h - 1);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const uint16_t* r0 = x + (static_cast<int64_t>(n) * h + y0) * w * C;
+  const uint16_t* r1 = x + (static_cast<int64_t>(n) * h + y1) * w * C;
+  uint16_t* orow = out + static_cast<int64_t>(row) * W * C;
+  const int half = C / 2;
+  const int items = W * cv;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int ox = i / cv, c8 = i - ox * cv;
+    const float fx = sx * ox;
+    const int x0 = static_cast<int>(fx);
+    const int x1 = min(x0 + 1, w - 1);
+    const float lx = fx - x0, hx = 1.f - lx;
+    const uint4 ua = __ldg(reinterpret_cast<const uint4*>(r0 + x0 * C + c8 * 8));
+    const uint4 ub = __ldg(reinterpret_cast<const uint4*>(r0 + x1 * C + c8 * 8));
+    const uint4 uc = __ldg(reinterpret_cast<const uint4*>(r1 + x0 * C + c8 * 8));
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(r1 + x1 * C + c8 * 8));
+    const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+    const uint32_t wc[4] = {uc.x, uc.y, uc.z, uc.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+    const float2 hx2 = make_float2(hx, hx), lx2 = make_float2(lx, lx), hy2 = make_float2(hy, hy), ly2 = make_float2(ly, ly);
+    float2 o[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * c[k] + lx * d[k]);
-    if (tabx) {
-      const int ch = c8 * 8, half = C / 2;
-      const float* t = ch < half ? tabx + static_cast<int64_t>(ox) * half + ch
-                                 : taby + static_cast<int64_t>(oy) * half + (ch - half);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] += __ldg(t + k);
+    for (int k = 0; k < 4; ++k) {
+      // hy * (hx * a + lx * b) + ly * (hx * c + lx * d), operation for operation as the scalar form
+      const float2 top = ffma2(lx2, cvt16x2<BF16>(wb[k]), fmul2(hx2, cvt16x2<BF16>(wa[k])));
+      const float2 bot = ffma2(lx2, cvt16x2<BF16>(wd[k]), fmul2(hx2, cvt16x2<BF16>(wc[k])));
+      o[k] = ffma2(ly2, bot, fmul2(hy2, top));
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * H + oy) * W + ox) * C + c8 * 8) = pack8<BF16>(o);
+    if (tabx) {
+      const int ch = c8 * 8;
+      const float* t = ch < half ? tabx + ox * half + ch : taby + oy * half + (ch - half);
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(t)), t1 = __ldg(reinterpret_cast<const float4*>(t) + 1);
+      o[0] = fadd2(o[0], make_float2(t0.x, t0.y)); o[1] = fadd2(o[1], make_float2(t0.z, t0.w));
+      o[2] = fadd2(o[2], make_float2(t1.x, t1.y)); o[3] = fadd2(o[3], make_float2(t1.z, t1.w));
+    }
+    uint4 u;
+    u.x = pack16x2<BF16>(o[0].x, o[0].y); u.y = pack16x2<BF16>(o[1].x, o[1].y);
+    u.z = pack16x2<BF16>(o[2].x, o[2].y); u.w = pack16x2<BF16>(o[3].x, o[3].y);
+    *reinterpret_cast<uint4*>(orow + ox * C + c8 * 8) = u;
   }
 }
 
@@ -324,10 +345,11 @@ extern "C" int iggt_upsample_bilinear_nhwc(const void* x, void* out, int NB, int
                                            const float* tabx, const float* taby, int dtype, iggt_stream_t stream) {
   if (NB <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || (C % 16)) return -1;
   if ((tabx == nullptr) != (taby == nullptr)) return -1;
-  const int64_t total = static_cast<int64_t>(NB) * H * W * (C / 8);
-  if (dtype) upsample_bilinear_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  if (static_cast<int64_t>(NB) * H > 0x7fffffff || static_cast<int64_t>(w) * C > 0x7fffffff) return -1;
+  const unsigned rows = static_cast<unsigned>(NB) * H;                 // one CTA per output row
+  if (dtype) upsample_bilinear_kernel<true><<<rows, 256, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)x, (uint16_t*)out, NB, h, w, H, W, C, tabx, taby);
-  else upsample_bilinear_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  else upsample_bilinear_kernel<false><<<rows, 256, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)x, (uint16_t*)out, NB, h, w, H, W, C, tabx, taby);
   return (int)cudaGetLastError();
 }

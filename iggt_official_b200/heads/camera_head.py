@@ -1,17 +1,22 @@
 """B200-native camera head: iterative pose refinement on the S camera tokens
 (reference: iggt/heads/camera_head.py:83-154, iggt/heads/head_act.py:12-35).
 
-M = B*S rows of width 2048 against 216 M parameters: every Linear is weight-bandwidth bound, so they run
-on the weight-streaming `iggt_skinny_gemm` (fp32 activations, 16-bit weights, fp32 accumulate) and the
-S x S attention on `iggt_small_attention`; LayerNorms use `iggt_layernorm` (fp32 out).  The AdaLN modulate
-(a few [B*S, 2048] elementwise ops) is expressed with torch tensor arithmetic.
+M = B*S rows of width 2048 against 216 M parameters: every Linear is a weight stream (fp32 activations, 16-bit
+weights, fp32 accumulate).  For B*S <= 16 the whole head - 4 iterations x (embed, AdaLN, 4 blocks, pose branch) - is ONE
+persistent launch (`iggt_camera_head`, csrc/camera.cu: the producer warp streams weights across phase boundaries, a
+device-wide barrier separates the ~27 phases of an iteration).  Larger batches (and IGGT_CAMERA_FUSED=0) run layer by
+layer: `iggt_skinny_gemm`, `iggt_small_attention`, `iggt_layernorm`, with the AdaLN modulate in torch arithmetic.
 """
+import ctypes
+import os
 from typing import List
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..layout import Node
+
+FUSED = os.environ.get("IGGT_CAMERA_FUSED", "1") != "0"
 
 DIM = 2048
 HEADS = 16
@@ -55,8 +60,28 @@ class CameraHead(Node):
         pk["pb1_w"], pk["pb1_b"] = h16(self.pose_branch.fc1.weight), _f32(self.pose_branch.fc1.bias, device)
         pk["pb2_w"], pk["pb2_b"] = h16(self.pose_branch.fc2.weight), _f32(self.pose_branch.fc2.bias, device)
         pk["empty"] = _f32(self.empty_pose_tokens, device).reshape(1, 9)
+        e16 = torch.zeros(16, dtype=torch.float32, device=device)
+        e16[:9] = pk["empty"].view(-1)
+        pk["empty16"] = e16
+        pk["cstruct"] = self._cstruct(pk)
         self._pk, self._pk_key = pk, key
         return pk
+
+    @staticmethod
+    def _cstruct(pk):
+        """iggt_camera_weights for the one-launch kernel: raw pointers into the packed tensors (kept alive by `pk`)."""
+        w = _lib.CameraWeights()
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        w.emb_w, w.emb_b, w.mod_w, w.mod_b = P(pk["emb_w"]), P(pk["emb_b"]), P(pk["mod_w"]), P(pk["mod_b"])
+        for i in range(4):
+            t = pk[f"t{i}"]
+            for name in ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w",
+                         "fc2_b", "ls2"):
+                setattr(w.blk[i], name, P(t[name]))
+        w.tok_w, w.tok_b, w.trk_w, w.trk_b = P(pk["tok_w"]), P(pk["tok_b"]), P(pk["trk_w"]), P(pk["trk_b"])
+        w.pb1_w, w.pb1_b, w.pb2_w, w.pb2_b = P(pk["pb1_w"]), P(pk["pb1_b"]), P(pk["pb2_w"]), P(pk["pb2_b"])
+        w.empty = P(pk["empty16"])
+        return w
 
     @staticmethod
     def _rows(fn, x, *a, **k):
@@ -94,6 +119,12 @@ class CameraHead(Node):
         dt = compute_dtype or (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16)
         pk = self._packed(dt, dev)
         M = B * S
+        if FUSED and M <= 16 and camera_tokens.is_cuda:
+            rows = camera_tokens.reshape(M, C)                    # a strided view of tokens[:, :, 0]: no copy
+            if rows.dtype != torch.float32 or rows.stride(1) != 1:
+                rows = rows.float().contiguous()
+            poses = ops.camera_head(pk["cstruct"], pk, rows, B, S, num_iterations, dt)
+            return [poses[i].view(B, S, 9) for i in range(num_iterations)]
         raw = camera_tokens.reshape(M, C).float().contiguous()
         pt = torch.empty_like(raw)
         ops.layernorm(raw, pk["tok_w"], pk["tok_b"], 1e-5, pt)

@@ -322,6 +322,24 @@ def small_attention(qkv, B, N, H, d):
     return out
 
 
+def camera_head(weights, keepalive, tokens, B, S, iters, dtype):
+    """The whole camera head in one persistent launch (csrc/camera.cu).  `weights`: a filled `_lib.CameraWeights`,
+    `keepalive`: the tensors it points to; `tokens`: fp32 camera-token rows [B*S, 2048] (any row pitch).  Returns
+    the activated pose encodings fp32 [iters, B*S, 9]."""
+    import ctypes
+    assert tokens.is_cuda and tokens.dtype == torch.float32 and tokens.dim() == 2 and tokens.shape[1] == 2048 and tokens.stride(1) == 1
+    M = B * S
+    assert tokens.shape[0] == M
+    ws_bytes = int(_lib.load().iggt_camera_head_workspace(M))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=tokens.device)
+    out = torch.empty((iters, M, 9), dtype=torch.float32, device=tokens.device)
+    wbytes = 2.0 * (2048 * 16 + 6144 * 2048 + 4 * (6144 * 2048 + 2048 * 2048 + 2 * 8192 * 2048) + 1024 * 2048 + 9 * 1024)
+    _call(tokens, "iggt_camera_head", 2.0 * M * iters * wbytes / 2, iters * wbytes,
+          ctypes.addressof(weights), tokens.data_ptr(), tokens.stride(0), out.data_ptr(), ws.data_ptr(), ws_bytes, B, S,
+          iters, F16 if dtype == torch.float16 else BF16, _STREAM)
+    return out
+
+
 def layernorm16(x, w, b, eps=1e-5, out=None):
     """LayerNorm over the last dim (64 / 128 / 256) of a contiguous 16-bit tensor."""
     assert x.is_cuda and x.is_contiguous()

@@ -157,6 +157,31 @@ int iggt_skinny_gemm(const float* x, int64_t ldx, const void* W, int64_t ldw, co
 int iggt_small_attention(const float* qkv, float* out, int B, int N, int H, int d, float scale,
                          iggt_stream_t stream);
 
+/* The whole camera head in ONE persistent launch (B*S <= 16 camera tokens; larger batches use iggt_skinny_gemm /
+ * iggt_small_attention per layer).  Replaces iggt/heads/camera_head.py:83-154 (`CameraHead.forward` + `trunk_fn`:
+ * token_norm, 4 x [embed_pose -> SiLU + Linear -> AdaLN modulate -> 4 Blocks(2048, 16 heads) -> trunk_norm ->
+ * Mlp(2048 -> 1024 -> 9) -> accumulate]) and `activate_pose` (iggt/heads/head_act.py:12-35: ReLU on the FoV dims).
+ * All weight matrices are 16-bit row-major [N, K] (torch Linear layout); vectors fp32.  tokens: fp32 camera-token rows,
+ * row (b*S + s) at tokens + (b*S + s) * ld_tokens (ld_tokens = T*2048 reads layer 23's tokens[:, :, 0] in place).
+ * out: fp32 [iters][B*S][9].  workspace: iggt_camera_head_workspace(B*S) bytes, 16-byte aligned.
+ * Returns -7 when B*S > 16 (use the per-layer launchers). */
+typedef struct {
+  const float *n1w, *n1b; const void* qkv_w; const float* qkv_b; const void* proj_w; const float* proj_b; const float* ls1;
+  const float *n2w, *n2b; const void* fc1_w; const float* fc1_b; const void* fc2_w; const float* fc2_b; const float* ls2;
+} iggt_camera_block;
+typedef struct {
+  const void* emb_w; const float* emb_b;     /* embed_pose: [2048, 16] (K = 9 zero-padded to 16), [2048] */
+  const void* mod_w; const float* mod_b;     /* poseLN_modulation[1]: [6144, 2048] */
+  iggt_camera_block blk[4];
+  const float *tok_w, *tok_b, *trk_w, *trk_b;  /* token_norm, trunk_norm */
+  const void* pb1_w; const float* pb1_b;     /* pose_branch.fc1 [1024, 2048] */
+  const void* pb2_w; const float* pb2_b;     /* pose_branch.fc2 [9, 1024] */
+  const float* empty;                        /* empty_pose_tokens, 16 floats (9 valid, rest 0) */
+} iggt_camera_weights;
+int64_t iggt_camera_head_workspace(int M);
+int iggt_camera_head(const iggt_camera_weights* w, const float* tokens, int64_t ld_tokens, float* out, void* workspace,
+                     int64_t ws_bytes, int B, int S, int iters, int dtype, iggt_stream_t stream);
+
 /* ---- Part (instance-feature) path kernels. */
 
 /* LayerNorm (affine) over C in {64,128,256} channels of 16-bit rows -> 16-bit.

@@ -49,7 +49,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             res[name] = {"us": round(ms * 1e3, 1), "tflops": round(4.0 * ns * L * L * 1024 / ms / 1e9)}
     print(json.dumps(res))
 else:
-    emus = sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "1", "2", "3", "4"]
+    emus = sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "1"]
     allres = {}
     for i, emu in enumerate(emus):
         env = dict(os.environ, IGGT_ATTN_EMU=emu, SWEEP_SDPA="1" if i == 0 else "0", SWEEP_SHARDED="1" if i == 0 or emu == emus[-1] else "0")

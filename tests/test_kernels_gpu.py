@@ -193,10 +193,11 @@ def test_attention_plan_is_used_and_cached(ops):
     assert ops.attention_plan(8, 1374, 1374, 16)[0] == 1
 
 
-@pytest.mark.parametrize("emu", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("emu", [0, 1])
 def test_attention_emulated_exp2_variants(emu):
-    """IGGT_ATTN_EMU (probability pairs per 8 on the packed FMA-pipe exp2) is read once per process: each variant runs
-    in a child process against the exact softmax, incl. a ragged last kv tile and a split-KV launch."""
+    """IGGT_ATTN_EMU (1 = two of every 8 probability pairs on the packed FMA-pipe exp2; off by default, measured no
+    faster) is read once per process: each variant runs in a child process against the exact softmax, incl. a ragged
+    last kv tile and a split-KV launch."""
     import os
     import subprocess
     import sys
