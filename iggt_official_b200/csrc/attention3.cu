@@ -598,7 +598,7 @@ namespace {
 // Cost (in kv-tile steps of one CTA, ~1.4 us) of running the launch with `splits` kv ranges on `sms` CTAs: rounds x (tiles
 // per split + a fixed per-item overhead: Q load, pipeline fill, first-tile max, O read-out) + the merge pass over the fp32
 // workspace.  Constants fitted to the B200 sweep profiles/r02b_attn_sweep.json (1 of 8 / 4 / 2 views against 8 views of
-// keys, 1..5 splits): 7 steps per item, 10 steps + traffic for the merge launch; predictions within 6 % of measured.
+// keys, 1..5 splits): 7 steps per item, 8 steps + traffic for the merge launch; predictions within 6 % of measured.
 double attn3_cost(int num_seq, int Lq, int Lk, int H, int splits, int sms) {
   const int q_tiles = (Lq + A3_BQ - 1) / A3_BQ, n_kv = (Lk + A3_BK - 1) / A3_BK;
   const int tps = (n_kv + splits - 1) / splits, se = (n_kv + tps - 1) / tps;
@@ -615,7 +615,7 @@ double attn3_cost(int num_seq, int Lq, int Lk, int H, int splits, int sms) {
   double cost = rounds * (tps + 7.0);
   if (se > 1) {
     const double ws_bytes = 2.0 * se * num_seq * Lq * H * A3_D * 4;     // written + read back
-    cost += 10.0 + ws_bytes / 4.0e12 / 1.4e-6;                           // ~4 TB/s through L2, 1.4 us per kv-tile step
+    cost += 8.0 + ws_bytes / 8.0e12 / 1.4e-6;                            // workspace stays in L2; 1.4 us per kv-tile step
   }
   return cost;
 }
@@ -630,7 +630,7 @@ int attn3_plan_splits(int num_seq, int Lq, int Lk, int H, int sms) {
     double bc = attn3_cost(num_seq, Lq, Lk, H, 1, sms);
     for (int s = 2; s <= 8 && s <= n_kv; ++s) {
       const double c = attn3_cost(num_seq, Lq, Lk, H, s, sms);
-      if (c < 0.93 * bc) { bc = c; best = s; }        // a split must buy at least 7 %
+      if (c < 0.95 * bc) { bc = c; best = s; }        // a split must buy at least 5 %
     }
   }
   const int tps = (n_kv + best - 1) / best;
