@@ -58,8 +58,14 @@ struct CamProgram {
   CamPhase ph[CAM_MAX_PHASES];
   int n_phases, iters, M, Mpad, B, S;
   unsigned* barrier;           // zeroed before the launch
+  unsigned long long* dbg;     // optional (IGGT_CAMERA_DEBUG=1): CTA 0 stamps %globaltimer at 4 points of every phase
 };
 
+__device__ __forceinline__ unsigned long long cam_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -156,6 +162,8 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
     for (int p = 0; p < prog.n_phases; ++p) {
       const CamPhase& P = prog.ph[p];
       if ((P.flags & CF_ONCE) && it > 0) continue;
+      unsigned long long* stamp = (prog.dbg && cta == 0 && tid == 0) ? prog.dbg + (it * CAM_MAX_PHASES + p) * 4 : nullptr;
+      if (stamp) stamp[0] = cam_now();
       if (P.type == PH_GEMM) {
         const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
         const int nchunks = (P.K + KX - 1) / KX;                         // activation chunks of KX
@@ -206,6 +214,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
                 }
               }
               named_bar_sync(2, 256);
+              if (stamp && t == cta && ch == 0) stamp[1] = cam_now();
             }
             // ---- weight stages of this chunk
             for (int kb = 0; kb < kn / CAM_KC; ++kb) {
@@ -328,7 +337,9 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
           }
         }
       }
+      if (stamp) stamp[2] = cam_now();
       cam_grid_sync(prog.barrier, target);
+      if (stamp) stamp[3] = cam_now();
     }
 }
 
@@ -346,7 +357,7 @@ int64_t cam_ws_floats(int M) { return static_cast<int64_t>(M) * (5 * CAM_DIM + 2
 
 extern "C" int64_t iggt_camera_head_workspace(int M) {
   if (M <= 0) return -1;
-  return cam_ws_floats(M) * 4 + 256;
+  return cam_ws_floats(M) * 4 + 256 + 8 * CAM_MAX_PHASES * 4 * 8;     // + debug stamps [8 iters][32 phases][4]
 }
 
 extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* tokens, int64_t ld_tokens, float* out,
@@ -371,6 +382,7 @@ extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* token
   ws.hdn = p; p += M * 1024;
   ws.pred = p; p += M * 16;
   ws.barrier = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(p) + 127) & ~static_cast<uintptr_t>(127));
+  static const int dbg_env = [] { const char* e = getenv("IGGT_CAMERA_DEBUG"); return e ? atoi(e) : 0; }();
   cudaError_t e = cudaMemsetAsync(ws.barrier, 0, 4, s);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(ws.pred, 0, M * 16 * 4, s);       // columns 9..15 of `pred` are the zero padding of embed_pose's K
@@ -378,6 +390,7 @@ extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* token
 
   CamProgram prog{};
   prog.iters = iters; prog.M = M; prog.Mpad = M <= 8 ? 8 : 16; prog.B = B; prog.S = S; prog.barrier = ws.barrier;
+  prog.dbg = (dbg_env && iters <= 8) ? reinterpret_cast<unsigned long long*>(ws.barrier + 32) : nullptr;   // +128 B
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   int nmaps = 0;
   auto add_map = [&](const void* W, int N, int K) -> int {

@@ -53,6 +53,13 @@ struct GemmParams {
   int act_post;
   // EPI_RESID32: round (acc + bias) to 16 bit before the LayerScale multiply (autocast Linear output)
   int round_out16;
+  // EPI_QKV, view sharding: the K | V column chunks (col >= gather_col0) of every tile are ALSO stored through these
+  // tensor maps (device array; one per rank of the box, each describing THIS rank's row window of that rank's gathered
+  // K|V buffer, reached over NVLink peer mappings): the all-gather of the global attention's keys and values is fused
+  // into the producing GEMM, tile by tile (parallel.py, FusedKVGather)
+  const CUtensorMap* gather_maps;
+  int n_gather;
+  int gather_col0;
   // stream-K (EPI_RESID32 only): the (tile, k-block) space is cut into gridDim.x equal contiguous ranges; every
   // CTA reduce-adds the partial product of each tile segment it owns (fp32 atomics in L2 make the pieces add up)
   int stream_k;
@@ -482,6 +489,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (leader) {
             if constexpr (CONV) tma_store_4d(&tmC, stg, col0, x0, y0, img);
             else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
+            if constexpr (EPI == EPI_QKV) {
+              if (p.n_gather > 0 && col0 >= p.gather_col0)               // K | V chunk: to every rank's gathered buffer too
+                for (int r = 0; r < p.n_gather; ++r)
+                  tma_store_2d(&p.gather_maps[r], stg, col0 - p.gather_col0, mt * GEMM_BM);
+            }
             tma_store_commit();
           }
           ++store_count;
@@ -550,7 +562,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (leader) tma_store_wait_all<0>();
+    if (leader) {
+      tma_store_wait_all<0>();
+      if constexpr (EPI == EPI_QKV) {
+        if (p.n_gather > 0) __threadfence_system();      // peer stores visible before the cross-rank barrier
+      }
+    }
   }
 
   tc_fence_before();

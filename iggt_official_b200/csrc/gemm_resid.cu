@@ -43,7 +43,8 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
                              int64_t ldo, int M, int C, int K, int dtype, const float* bias,
                              int qk_norm, const float* qn_w, const float* qn_b, const float* kn_w,
                              const float* kn_b, const float* rope_cos, const float* rope_sin,
-                             const int* pos_yx, int T, iggt_stream_t stream) {
+                             const int* pos_yx, int T, const void* gather_maps, int n_gather,
+                             iggt_stream_t stream) {
   if (M <= 0 || C <= 0 || K <= 0 || (C % 64)) return -1;
   if ((lda % 8) || (ldw % 8) || (K % 8) || (ldo % 8)) return -2;
   if (dtype != 0 && dtype != 1) return -3;
@@ -55,6 +56,8 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   p.qk_norm = qk_norm; p.C = C;
   p.qn_w = qn_w; p.qn_b = qn_b; p.kn_w = kn_w; p.kn_b = kn_b;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.pos_yx = pos_yx; p.T = T > 0 ? T : 1;
+  if (n_gather < 0 || n_gather > 16 || (n_gather > 0 && !gather_maps)) return -1;
+  p.gather_maps = static_cast<const CUtensorMap*>(gather_maps); p.n_gather = n_gather; p.gather_col0 = C;
   const GemmPlan plan = plan_gemm(EPI_QKV, M, N, K);
   const int bn = plan.bn;
   const bool pair = plan.pair != 0;
@@ -66,4 +69,18 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   if (make_tmap_2d(&tC, dt, qkv, M, N, ldo, 64, GEMM_BM)) return -4;
   return dtype ? dispatch_bn<EPI_QKV, true>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream)
                : dispatch_bn<EPI_QKV, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
+}
+
+// Tensor maps for the fused K|V gather: dst[i] = address of THIS rank's row window inside rank i's gathered K|V buffer
+// ([rows, cols] 16-bit, row pitch ld elements; peer-mapped pointers).  Writes n maps (128 bytes each) to `dev_maps`
+// (device memory, 64-byte aligned) with a synchronous copy - call once at setup, not inside a graph capture.
+extern "C" int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int dtype,
+                                   void* dev_maps) {
+  if (!dst || !dev_maps || n <= 0 || n > 16 || rows <= 0 || cols <= 0 || (ld % 8) || (dtype != 0 && dtype != 1)) return -1;
+  CUtensorMap maps[16];
+  for (int i = 0; i < n; ++i)
+    if (make_tmap_2d(&maps[i], dtype ? TM_BF16 : TM_F16, dst[i], (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, 64,
+                     GEMM_BM))
+      return -4;
+  return (int)cudaMemcpy(dev_maps, maps, sizeof(CUtensorMap) * n, cudaMemcpyHostToDevice);
 }

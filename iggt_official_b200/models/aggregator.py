@@ -140,11 +140,12 @@ class Aggregator(Node):
         dt = w.qkv_w.dtype
         h = torch.empty((M, 1024), dtype=dt, device=x.device)
         ops.layernorm(x, w.n1w, w.n1b, eps, h)
+        fused = kv_gather.gemm_args() if hasattr(kv_gather, "gemm_args") else {}   # K|V gather fused into this GEMM
         if rope is None:
             qkv = ops.gemm_qkv(h, w.qkv_w, w.qkv_b, 1024)
         else:
             qkv = ops.gemm_qkv(h, w.qkv_w, w.qkv_b, 1024, qk_norm=True, qn_w=w.qn_w, qn_b=w.qn_b, kn_w=w.kn_w,
-                               kn_b=w.kn_b, rope_cos=rope[0], rope_sin=rope[1], pos_yx=rope[2], T=T)
+                               kn_b=w.kn_b, rope_cos=rope[0], rope_sin=rope[1], pos_yx=rope[2], T=T, **fused)
         q = qkv[:, :1024]
         if kv_gather is None:
             k, v, Lk = qkv[:, 1024:2048], qkv[:, 2048:], Lq
@@ -201,8 +202,9 @@ class Aggregator(Node):
         S_tot = total_views if total_views is not None else S * world
         gather = None
         if world > 1:
-            from ..parallel import make_kv_gather
-            gather = make_kv_gather(group, world, B, S, T)
+            from ..parallel import make_fused_kv_gather, make_kv_gather
+            gather = make_fused_kv_gather(group, world, view_offset // S, B, S, T, dt, dev) or \
+                make_kv_gather(group, world, B, S, T)
         for i in range(24):
             self._block(y, pk["frame"][i], 1e-5, NI, T, T, rope)
             if i in keep:

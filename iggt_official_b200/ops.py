@@ -112,7 +112,7 @@ def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
 
 
 def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b=None, rope_cos=None,
-             rope_sin=None, pos_yx=None, T=0, out=None):
+             rope_sin=None, pos_yx=None, T=0, out=None, gather_maps=None, n_gather=0):
     _chk2d(a); _chk2d(w)
     M, K = a.shape
     if out is None:
@@ -121,8 +121,22 @@ def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, C, K, _dt(a), _ptr(bias), 1 if qk_norm else 0,
                                    _ptr(qn_w), _ptr(qn_b), _ptr(kn_w), _ptr(kn_b), _ptr(rope_cos),
-                                   _ptr(rope_sin), _ptr(pos_yx), T, _STREAM)
+                                   _ptr(rope_sin), _ptr(pos_yx), T, _ptr(gather_maps), n_gather, _STREAM)
     return out
+
+
+def kv_gather_maps(dst_windows, rows, cols, ld, dtype, device):
+    """Device array of tensor maps for the fused K|V gather: dst_windows[i] = THIS rank's [rows, cols] window (row pitch
+    ld) inside rank i's gathered buffer, as a (peer-mapped) CUDA tensor or an integer device address."""
+    import ctypes
+    n = len(dst_windows)
+    ptrs = (ctypes.c_void_p * n)(*[d if isinstance(d, int) else d.data_ptr() for d in dst_windows])
+    dev = torch.empty(n * 128, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        st = _lib.load().iggt_kv_gather_maps(ctypes.cast(ptrs, ctypes.c_void_p), n, rows, cols, ld,
+                                            F16 if dtype == torch.float16 else BF16, dev.data_ptr())
+    _lib.check(st, "iggt_kv_gather_maps")
+    return dev
 
 
 def conv_nhwc(x, wp, bias=None, act=0, resid=None, taps=9, out=None, resid2=None, act_post=0):
@@ -322,7 +336,7 @@ def small_attention(qkv, B, N, H, d):
     return out
 
 
-def camera_head(weights, keepalive, tokens, B, S, iters, dtype):
+def camera_head(weights, keepalive, tokens, B, S, iters, dtype, return_workspace=False):
     """The whole camera head in one persistent launch (csrc/camera.cu).  `weights`: a filled `_lib.CameraWeights`,
     `keepalive`: the tensors it points to; `tokens`: fp32 camera-token rows [B*S, 2048] (any row pitch).  Returns
     the activated pose encodings fp32 [iters, B*S, 9]."""
@@ -337,7 +351,7 @@ def camera_head(weights, keepalive, tokens, B, S, iters, dtype):
     _call(tokens, "iggt_camera_head", 2.0 * M * iters * wbytes / 2, iters * wbytes,
           ctypes.addressof(weights), tokens.data_ptr(), tokens.stride(0), out.data_ptr(), ws.data_ptr(), ws_bytes, B, S,
           iters, F16 if dtype == torch.float16 else BF16, _STREAM)
-    return out
+    return (out, ws) if return_workspace else out
 
 
 def layernorm16(x, w, b, eps=1e-5, out=None):
