@@ -26,8 +26,8 @@ SIGNATURES = {
                           c_void_p, c_int, c_void_p],
     "iggt_gemm_qkv": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                      c_int, c_void_p, c_int, c_void_p],
-    "iggt_kv_gather_maps": [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_void_p],
+                      c_int, c_void_p, c_int, c_int, c_void_p],
+    "iggt_kv_gather_maps": [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
     "iggt_conv_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "iggt_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,

@@ -10,10 +10,14 @@
 //     ({256 k, 16 columns}, 8 KB) of the next phases stream into an 8-stage ring while the consumers are still in the
 //     barrier of the current one - weights do not depend on activations - so HBM stays busy across phase boundaries;
 //   * activations are tiny and live in L2: after each barrier the 8 consumer warps pull the phase's input rows
-//     ([M, <= 2048] fp32) into shared memory, applying the LayerNorm that precedes the Linear on the way (statistics over
-//     the row, two-pass in registers), stored k-major / row-minor so that a thread's fma pairs are packed (FFMA2);
-//   * consumer warp w owns 2 of the tile's 16 columns for all M rows; lanes split k; one butterfly reduction per tile;
-//     bias, exact-erf GELU / SiLU, LayerScale, residual and the pose accumulation + activation ride in the epilogue;
+//     ([M, <= 2048] fp32, 16-byte vectors) into shared memory, applying the LayerNorm that precedes the Linear on the way
+//     (statistics over the row, two-pass in registers);
+//   * every weight and every activation element is read from shared memory ONCE per tile: warp w owns a 32-wide k slice of
+//     each 256-wide stage, a lane owns one row and 8 (16) consecutive k of that slice and accumulates all 16 columns
+//     (packed FFMA2 over k pairs); partial sums meet through two shuffle rounds and an 8 KB shared-memory reduction.
+//     (A first version gave each warp 2 columns and made all 8 warps re-read the activations: 64 KB of shared-memory
+//     reads per 8 KB of weights - the timeline showed 1.3 TB/s of weight streaming.)
+//   * bias, exact-erf GELU / SiLU, LayerScale, residual and the pose accumulation + activation ride in the epilogue;
 //   * the S x S attention (16 heads x 128) is a phase of its own: one warp per (row, head).
 // fp32 activations and accumulation, 16-bit weights - the arithmetic of iggt_skinny_gemm / iggt_small_attention, which
 // this kernel replaces for M <= 16 (larger B*S keep the per-layer launches).
@@ -32,7 +36,8 @@ constexpr int CAM_KC = 256;                   // k per weight stage
 constexpr int CAM_STAGES = 8;
 constexpr int CAM_W_BYTES = CAM_COLS * CAM_KC * 2;       // 8 KB
 constexpr int CAM_X_FLOATS = 16384;           // activation buffer: [k][Mpad] fp32, 64 KB
-constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + 256;
+constexpr int CAM_RED_FLOATS = 8 * 16 * CAM_COLS;         // cross-warp reduction buffer [8 warps][<= 16 rows][16 cols]
+constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + CAM_RED_FLOATS * 4 + 256;
 constexpr int CAM_MAX_PHASES = 32, CAM_MAX_MAPS = 24;
 
 enum CamPhaseType : int { PH_GEMM = 0, PH_ATTN = 1, PH_MODULATE = 2, PH_LNROWS = 3 };
@@ -100,11 +105,6 @@ __device__ __forceinline__ void cam_unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
-// Position of activation k inside the staged buffer: a consumer lane owns the 8 consecutive k of its uint4 of weights
-// (k = 8 * lane + j inside a 256-wide stage); storing them at (j * 32 + lane) makes the lanes' 32-byte row groups
-// consecutive in shared memory for every j (conflict-free LDS.128) instead of 256 bytes apart (8-way conflicts).
-__device__ __forceinline__ int cam_perm(int k) { return (k & ~255) | ((k & 7) << 5) | ((k >> 3) & 31); }
-
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -118,7 +118,8 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
   extern __shared__ __align__(128) uint8_t cam_smem[];
   uint8_t* sW = cam_smem;
   float* xs = reinterpret_cast<float*>(cam_smem + CAM_STAGES * CAM_W_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4);
+  float* red = xs + CAM_X_FLOATS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + (CAM_X_FLOATS + CAM_RED_FLOATS) * 4);
   uint64_t* empty = full + CAM_STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -168,49 +169,62 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
         const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
         const int nchunks = (P.K + KX - 1) / KX;                         // activation chunks of KX
         const bool embed0 = (P.flags & CF_EMBED_IN) && it == 0;
+        // lane = (row m, k group kq): warp w owns k in [32 w, 32 w + 32) of every 256-wide stage, split over KQ lane
+        // groups of KL consecutive k; every lane accumulates ALL 16 columns of the tile for its row.
+        constexpr int KQ = 32 / MP;                                       // 4 (MP = 8) or 2 (MP = 16)
+        constexpr int KL = 32 / KQ;                                       // 8 or 16 consecutive k per lane and stage
+        const int lm = lane % MP, kq = lane / MP;
         for (int t = cta; t < tiles; t += G) {
-          float2 acc[2][MP / 2];
+          float2 acc[CAM_COLS];                                           // (even k, odd k) partial sums per column
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int m = 0; m < MP / 2; ++m) acc[c][m] = make_float2(0.f, 0.f);
+          for (int c = 0; c < CAM_COLS; ++c) acc[c] = make_float2(0.f, 0.f);
           for (int ch = 0; ch < nchunks; ++ch) {
             const int k0 = ch * KX;
             const int kn = min(KX, ((P.K - k0 + CAM_KC - 1) / CAM_KC) * CAM_KC);   // staged k extent (multiple of 256)
             if (t == cta || nchunks > 1) {
-              // ---- stage the activations [M, kn] (k-major, row-minor), LayerNorm applied on the way
+              // ---- stage the activations [M, kn] as [k / 8][row][8] (16-byte vectors in and out), LayerNorm on the way
               named_bar_sync(2, 256);                                     // previous readers of xs are done
               for (int m = warp; m < MP; m += 8) {
                 if (m >= M) {
-                  for (int k = lane; k < kn; k += 32) xs[k * MP + m] = 0.f;          // (a permutation of [0, kn): any order)
+                  for (int k = lane * 4; k < kn; k += 128)
+                    *reinterpret_cast<float4*>(xs + ((k >> 3) * MP + m) * 8 + (k & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
                   continue;
                 }
                 const float* row = embed0 ? P.x2 : P.x + m * P.ldx;
-                if (P.ln) {                                               // K == 2048 == KX or 2 * KX
-                  float v[CAM_DIM / 32];
+                if (P.ln) {                                               // row length 2048; KX is 2048 or 1024
+                  float4 v[CAM_DIM / 128];
                   float s = 0.f;
 #pragma unroll
                   for (int i = 0; i < CAM_DIM / 128; ++i) {
-                    const float4 a = *reinterpret_cast<const float4*>(row + (lane + 32 * i) * 4);
-                    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
-                    s += (a.x + a.y) + (a.z + a.w);
+                    v[i] = *reinterpret_cast<const float4*>(row + (lane + 32 * i) * 4);
+                    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
                   }
                   const float mean = warp_sum_f(s) * (1.0f / CAM_DIM);
                   float q = 0.f;
 #pragma unroll
-                  for (int i = 0; i < CAM_DIM / 32; ++i) { const float d = v[i] - mean; q += d * d; }
+                  for (int i = 0; i < CAM_DIM / 128; ++i) {
+                    const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                    q += (a * a + bq * bq) + (c * c + d * d);
+                  }
                   const float rstd = rsqrtf(warp_sum_f(q) * (1.0f / CAM_DIM) + P.ln_eps);
 #pragma unroll
-                  for (int i = 0; i < CAM_DIM / 128; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const int k = (lane + 32 * i) * 4 + j;
-                      float y = (v[4 * i + j] - mean) * rstd;
-                      if (P.ln == 1) y = y * P.ln_w[k] + P.ln_b[k];
-                      if (k >= k0 && k < k0 + kn) xs[cam_perm(k - k0) * MP + m] = y;
+                  for (int i = 0; i < CAM_DIM / 128; ++i) {
+                    const int k = (lane + 32 * i) * 4;
+                    if (k < k0 || k >= k0 + kn) continue;
+                    float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd,
+                                           (v[i].w - mean) * rstd);
+                    if (P.ln == 1) {
+                      const float4 ww = *reinterpret_cast<const float4*>(P.ln_w + k), bb = *reinterpret_cast<const float4*>(P.ln_b + k);
+                      y.x = y.x * ww.x + bb.x; y.y = y.y * ww.y + bb.y; y.z = y.z * ww.z + bb.z; y.w = y.w * ww.w + bb.w;
                     }
+                    const int kk = k - k0;
+                    *reinterpret_cast<float4*>(xs + ((kk >> 3) * MP + m) * 8 + (kk & 7)) = y;
+                  }
                 } else {
-                  for (int k = lane; k < kn; k += 32) xs[cam_perm(k) * MP + m] = (k0 + k < P.K) ? row[k0 + k] : 0.f;
+                  for (int k = lane * 4; k < kn; k += 128) {             // P.K is a multiple of 4 (16, 1024, 2048, 8192)
+                    const float4 y = (k0 + k < P.K) ? *reinterpret_cast<const float4*>(row + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(xs + ((k >> 3) * MP + m) * 8 + (k & 7)) = y;
+                  }
                 }
               }
               named_bar_sync(2, 256);
@@ -219,21 +233,23 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             // ---- weight stages of this chunk
             for (int kb = 0; kb < kn / CAM_KC; ++kb) {
               mbar_wait(&full[st], ph);
-              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (warp * 2) * CAM_KC + lane * 8;
-              const float* xk = xs + (kb * CAM_KC + lane) * MP;            // cam_perm: element j of this lane at + j * 32 rows
-              float w0[8], w1[8];
-              cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w), w0);
-              cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + CAM_KC), w1);
+              const int kl = warp * 32 + kq * KL;                         // first k of this lane inside the stage
+              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + kl;
+              const float* xk = xs + (((kb * CAM_KC + kl) >> 3) * MP + lm) * 8;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 wa = make_float2(w0[j], w0[j]), wb = make_float2(w1[j], w1[j]);
+              for (int g8 = 0; g8 < KL / 8; ++g8) {                       // 8 k at a time
+                const float4 xa = *reinterpret_cast<const float4*>(xk + g8 * MP * 8);
+                const float4 xb = *reinterpret_cast<const float4*>(xk + g8 * MP * 8 + 4);
+                const float2 x01 = make_float2(xa.x, xa.y), x23 = make_float2(xa.z, xa.w);
+                const float2 x45 = make_float2(xb.x, xb.y), x67 = make_float2(xb.z, xb.w);
 #pragma unroll
-                for (int m4 = 0; m4 < MP / 4; ++m4) {
-                  const float4 xv = *reinterpret_cast<const float4*>(xk + j * 32 * MP + m4 * 4);
-                  acc[0][2 * m4] = ffma2(make_float2(xv.x, xv.y), wa, acc[0][2 * m4]);
-                  acc[0][2 * m4 + 1] = ffma2(make_float2(xv.z, xv.w), wa, acc[0][2 * m4 + 1]);
-                  acc[1][2 * m4] = ffma2(make_float2(xv.x, xv.y), wb, acc[1][2 * m4]);
-                  acc[1][2 * m4 + 1] = ffma2(make_float2(xv.z, xv.w), wb, acc[1][2 * m4 + 1]);
+                for (int c = 0; c < CAM_COLS; ++c) {
+                  float wf[8];
+                  cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + c * CAM_KC + g8 * 8), wf);
+                  acc[c] = ffma2(make_float2(wf[0], wf[1]), x01, acc[c]);
+                  acc[c] = ffma2(make_float2(wf[2], wf[3]), x23, acc[c]);
+                  acc[c] = ffma2(make_float2(wf[4], wf[5]), x45, acc[c]);
+                  acc[c] = ffma2(make_float2(wf[6], wf[7]), x67, acc[c]);
                 }
               }
               __syncwarp();
@@ -241,19 +257,28 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
           }
-          // ---- reduce over the lanes' k slices; lane (c * MP + m) keeps column c, row m
-          float mine = 0.f;
+          // ---- reduce: lanes of a row over their k groups (shuffles), then the 8 warps' k slices through shared memory
+          float part[CAM_COLS];
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < CAM_COLS; ++c) {
+            float v = acc[c].x + acc[c].y;
 #pragma unroll
-            for (int m = 0; m < MP; ++m) {
-              float v = (m & 1) ? acc[c][m >> 1].y : acc[c][m >> 1].x;
-              v = warp_sum_f(v);
-              if (lane == c * MP + m) mine = v;
-            }
-          if (lane < 2 * MP) {
-            const int c = lane / MP, m = lane % MP;
-            const int n = t * CAM_COLS + warp * 2 + c;
+            for (int o = MP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            part[c] = v;
+          }
+          named_bar_sync(2, 256);                                         // the previous tile's sums have been read
+          if (kq == 0) {
+#pragma unroll
+            for (int c = 0; c < CAM_COLS; c += 4)
+              *reinterpret_cast<float4*>(red + (warp * MP + lm) * CAM_COLS + c) = make_float4(part[c], part[c + 1], part[c + 2], part[c + 3]);
+          }
+          named_bar_sync(2, 256);
+          if (tid < MP * CAM_COLS) {
+            const int m = tid / CAM_COLS, c = tid % CAM_COLS;
+            float mine = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) mine += red[(wv * MP + m) * CAM_COLS + c];
+            const int n = t * CAM_COLS + c;
             if (n < P.N && m < M) {
               float v = mine + (P.bias ? P.bias[n] : 0.f);
               if (P.act == 1) v = gelu_erf(v);

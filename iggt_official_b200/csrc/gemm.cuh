@@ -57,9 +57,13 @@ struct GemmParams {
   // tensor maps (device array; one per rank of the box, each describing THIS rank's row window of that rank's gathered
   // K|V buffer, reached over NVLink peer mappings): the all-gather of the global attention's keys and values is fused
   // into the producing GEMM, tile by tile (parallel.py, FusedKVGather)
+  // The maps are 3-D {2048 columns, rows of one scene, scenes}: the rank's rows (scene, view, token) land at
+  // (scene, rank, view, token) in the gathered buffer; a 128-row tile that straddles two scenes is stored twice, the
+  // second time with a negative row origin in the next scene (TMA clips both stores to their scene).
   const CUtensorMap* gather_maps;
   int n_gather;
   int gather_col0;
+  int gather_rows;     // rows of this rank per scene (S_loc * T)
   // stream-K (EPI_RESID32 only): the (tile, k-block) space is cut into gridDim.x equal contiguous ranges; every
   // CTA reduce-adds the partial product of each tile segment it owns (fp32 atomics in L2 make the pieces add up)
   int stream_k;
@@ -490,9 +494,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (CONV) tma_store_4d(&tmC, stg, col0, x0, y0, img);
             else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
             if constexpr (EPI == EPI_QKV) {
-              if (p.n_gather > 0 && col0 >= p.gather_col0)               // K | V chunk: to every rank's gathered buffer too
-                for (int r = 0; r < p.n_gather; ++r)
-                  tma_store_2d(&p.gather_maps[r], stg, col0 - p.gather_col0, mt * GEMM_BM);
+              if (p.n_gather > 0 && col0 >= p.gather_col0) {             // K | V chunk: to every rank's gathered buffer too
+                const int row0 = mt * GEMM_BM, scene = row0 / p.gather_rows, r0 = row0 - scene * p.gather_rows;
+                const bool straddles = r0 + GEMM_BM > p.gather_rows && row0 + GEMM_BM > (scene + 1) * p.gather_rows && (scene + 1) * p.gather_rows < p.M;
+                for (int r = 0; r < p.n_gather; ++r) {
+                  tma_store_3d(&p.gather_maps[r], stg, col0 - p.gather_col0, r0, scene);
+                  if (straddles) tma_store_3d(&p.gather_maps[r], stg, col0 - p.gather_col0, r0 - p.gather_rows, scene + 1);
+                }
+              }
             }
             tma_store_commit();
           }

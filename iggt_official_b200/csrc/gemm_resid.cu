@@ -43,7 +43,7 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
                              int64_t ldo, int M, int C, int K, int dtype, const float* bias,
                              int qk_norm, const float* qn_w, const float* qn_b, const float* kn_w,
                              const float* kn_b, const float* rope_cos, const float* rope_sin,
-                             const int* pos_yx, int T, const void* gather_maps, int n_gather,
+                             const int* pos_yx, int T, const void* gather_maps, int n_gather, int gather_rows,
                              iggt_stream_t stream) {
   if (M <= 0 || C <= 0 || K <= 0 || (C % 64)) return -1;
   if ((lda % 8) || (ldw % 8) || (K % 8) || (ldo % 8)) return -2;
@@ -56,8 +56,9 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   p.qk_norm = qk_norm; p.C = C;
   p.qn_w = qn_w; p.qn_b = qn_b; p.kn_w = kn_w; p.kn_b = kn_b;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.pos_yx = pos_yx; p.T = T > 0 ? T : 1;
-  if (n_gather < 0 || n_gather > 16 || (n_gather > 0 && !gather_maps)) return -1;
+  if (n_gather < 0 || n_gather > 16 || (n_gather > 0 && (!gather_maps || gather_rows <= 0 || M % gather_rows))) return -1;
   p.gather_maps = static_cast<const CUtensorMap*>(gather_maps); p.n_gather = n_gather; p.gather_col0 = C;
+  p.gather_rows = gather_rows > 0 ? gather_rows : M;
   const GemmPlan plan = plan_gemm(EPI_QKV, M, N, K);
   const int bn = plan.bn;
   const bool pair = plan.pair != 0;
@@ -71,16 +72,21 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
                : dispatch_bn<EPI_QKV, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
 }
 
-// Tensor maps for the fused K|V gather: dst[i] = address of THIS rank's row window inside rank i's gathered K|V buffer
-// ([rows, cols] 16-bit, row pitch ld elements; peer-mapped pointers).  Writes n maps (128 bytes each) to `dev_maps`
-// (device memory, 64-byte aligned) with a synchronous copy - call once at setup, not inside a graph capture.
-extern "C" int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int dtype,
-                                   void* dev_maps) {
-  if (!dst || !dev_maps || n <= 0 || n > 16 || rows <= 0 || cols <= 0 || (ld % 8) || (dtype != 0 && dtype != 1)) return -1;
+// Tensor maps for the fused K|V gather: dst[i] = address of THIS rank's first row inside rank i's gathered K|V buffer
+// ([scenes][world * rows][cols] 16-bit, row pitch ld elements; peer-mapped pointers); the map is 3-D {cols, rows, scenes}
+// with scene pitch `scene_ld` elements.  Writes n maps (128 bytes each) to `dev_maps` (device memory, 64-byte aligned)
+// with a synchronous copy - call once at setup, not inside a graph capture.
+extern "C" int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int64_t scenes,
+                                   int64_t scene_ld, int dtype, void* dev_maps) {
+  if (!dst || !dev_maps || n <= 0 || n > 16 || rows <= 0 || cols <= 0 || scenes <= 0 || (ld % 8) || (scene_ld % 8) ||
+      (dtype != 0 && dtype != 1))
+    return -1;
   CUtensorMap maps[16];
-  for (int i = 0; i < n; ++i)
-    if (make_tmap_2d(&maps[i], dtype ? TM_BF16 : TM_F16, dst[i], (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, 64,
-                     GEMM_BM))
-      return -4;
+  for (int i = 0; i < n; ++i) {
+    uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)scenes};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)scene_ld * 2};
+    uint32_t box[3] = {64, (uint32_t)GEMM_BM, 1};
+    if (make_tmap(&maps[i], dtype ? TM_BF16 : TM_F16, 3, dst[i], dims, str, box)) return -4;
+  }
   return (int)cudaMemcpy(dev_maps, maps, sizeof(CUtensorMap) * n, cudaMemcpyHostToDevice);
 }

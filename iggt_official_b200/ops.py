@@ -112,7 +112,7 @@ def gemm_resid32(a, w, x, bias=None, gamma=None, round_out16=False):
 
 
 def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b=None, rope_cos=None,
-             rope_sin=None, pos_yx=None, T=0, out=None, gather_maps=None, n_gather=0):
+             rope_sin=None, pos_yx=None, T=0, out=None, gather_maps=None, n_gather=0, gather_rows=0):
     _chk2d(a); _chk2d(w)
     M, K = a.shape
     if out is None:
@@ -121,19 +121,20 @@ def gemm_qkv(a, w, bias, C, qk_norm=False, qn_w=None, qn_b=None, kn_w=None, kn_b
           a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, C, K, _dt(a), _ptr(bias), 1 if qk_norm else 0,
                                    _ptr(qn_w), _ptr(qn_b), _ptr(kn_w), _ptr(kn_b), _ptr(rope_cos),
-                                   _ptr(rope_sin), _ptr(pos_yx), T, _ptr(gather_maps), n_gather, _STREAM)
+                                   _ptr(rope_sin), _ptr(pos_yx), T, _ptr(gather_maps), n_gather, gather_rows, _STREAM)
     return out
 
 
-def kv_gather_maps(dst_windows, rows, cols, ld, dtype, device):
-    """Device array of tensor maps for the fused K|V gather: dst_windows[i] = THIS rank's [rows, cols] window (row pitch
-    ld) inside rank i's gathered buffer, as a (peer-mapped) CUDA tensor or an integer device address."""
+def kv_gather_maps(dst_windows, rows, cols, ld, scenes, scene_ld, dtype, device):
+    """Device array of 3-D tensor maps {cols, rows, scenes} for the fused K|V gather: dst_windows[i] = THIS rank's first row
+    inside rank i's gathered buffer (row pitch ld, scene pitch scene_ld elements), as a (peer-mapped) CUDA tensor or an
+    integer device address."""
     import ctypes
     n = len(dst_windows)
     ptrs = (ctypes.c_void_p * n)(*[d if isinstance(d, int) else d.data_ptr() for d in dst_windows])
     dev = torch.empty(n * 128, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
-        st = _lib.load().iggt_kv_gather_maps(ctypes.cast(ptrs, ctypes.c_void_p), n, rows, cols, ld,
+        st = _lib.load().iggt_kv_gather_maps(ctypes.cast(ptrs, ctypes.c_void_p), n, rows, cols, ld, scenes, scene_ld,
                                             F16 if dtype == torch.float16 else BF16, dev.data_ptr())
     _lib.check(st, "iggt_kv_gather_maps")
     return dev

@@ -52,54 +52,65 @@ def make_kv_gather(group, world: int, B: int, S_loc: int, T: int):
 
 
 class FusedKVGather:
-    """The same gather WITHOUT a collective on the data path (IGGT_FUSED_GATHER=1, one scene per call): every rank owns a
-    symmetric buffer [2 parities, S*T, 2048] (torch symmetric memory: the buffers of all ranks are mapped into every
-    process over NVLink / NVSwitch), and the qkv GEMM of a global block stores the K | V chunks of each finished tile
-    straight into ALL ranks' buffers through per-rank tensor maps (csrc/gemm.cuh, gather_maps; TMA stores to peer
-    memory) - the transfer rides under the GEMM tile by tile instead of a staging copy + NCCL all-gather afterwards.
-    What is left between GEMM and attention is a barrier on the symmetric-memory signal pads (capturable in the CUDA
-    graph).  Two parities: block l+2 may only overwrite parity p once every rank has finished reading block l's keys,
-    which the barrier of block l+1 guarantees."""
+    """The same gather WITHOUT a collective on the data path (default when torch symmetric memory is available;
+    IGGT_FUSED_GATHER=0 selects the NCCL all-gather): every rank owns a symmetric buffer [2 parities, B, S*T, 2048]
+    (the buffers of all ranks are mapped into every process over NVLink / NVSwitch), and the qkv GEMM of a global block
+    stores the K | V chunks of each finished tile straight into ALL ranks' buffers through per-rank tensor maps
+    (csrc/gemm.cuh, gather_maps; TMA stores to peer memory) - the transfer rides under the GEMM tile by tile instead of a
+    staging copy + NCCL all-gather afterwards, and the rows land in (scene, rank, view, token) order, i.e. already in the
+    layout the attention kernel reads.  What is left between GEMM and attention is a barrier on the symmetric-memory
+    signal pads (capturable in the CUDA graph).  Two parities: block l+2 may only overwrite parity p once every rank has
+    finished reading block l's keys, which the barrier of block l+1 guarantees.
+    Measured on 2 x B200 (profiles/r02d_*): C2 step 33.7 -> 32.4 ms; exchange 2.41 ms (NCCL) -> 0.48 ms (barriers)."""
 
-    def __init__(self, group, world: int, rank: int, S_loc: int, T: int, dtype, device):
+    def __init__(self, group, world: int, rank: int, B: int, S_loc: int, T: int, dtype, device):
         import torch.distributed._symmetric_memory as symm_mem
-        self.group, self.world = group, world
-        self.M_loc = S_loc * T
-        self.Lk = world * self.M_loc
-        self.buf = symm_mem.empty((2, self.Lk, 2048), dtype=dtype, device=device)
+        self.group, self.world, self.B = group, world, B
+        self.M_loc = S_loc * T                        # this rank's rows per scene
+        self.Lk = world * self.M_loc                  # keys per scene
+        shape = (2, B, self.Lk, 2048)
+        self.buf = symm_mem.empty(shape, dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.maps = []
         for parity in range(2):
             windows = []
             for r in range(world):
-                peer = self.hdl.get_buffer(r, (2, self.Lk, 2048), dtype)
-                windows.append(peer[parity, rank * self.M_loc:(rank + 1) * self.M_loc])
-            self.maps.append(ops.kv_gather_maps(windows, self.M_loc, 2048, 2048, dtype, device))
+                peer = self.hdl.get_buffer(r, shape, dtype)
+                windows.append(peer[parity, 0, rank * self.M_loc:])          # first row of this rank's window
+            self.maps.append(ops.kv_gather_maps(windows, self.M_loc, 2048, 2048, B, self.Lk * 2048, dtype, device))
         self.parity = 0
 
     def gemm_args(self):
-        return {"gather_maps": self.maps[self.parity], "n_gather": self.world}
+        return {"gather_maps": self.maps[self.parity], "n_gather": self.world, "gather_rows": self.M_loc}
 
     def __call__(self, qkv: torch.Tensor):
         ev = _trace_begin()
         self.hdl.barrier(channel=self.parity)        # every rank's tiles have landed in every buffer
         _trace_end(ev, "symm_barrier_kv", 0.0)
-        kv = self.buf[self.parity]
+        kv = self.buf[self.parity].view(self.B * self.Lk, 2048)
         self.parity ^= 1
         return kv[:, :1024], kv[:, 1024:], self.Lk
 
 
 _FUSED = {}
+_FUSED_FAILED = []
 
 
 def make_fused_kv_gather(group, world: int, rank: int, B: int, S_loc: int, T: int, dtype, device):
-    """FusedKVGather when it applies (IGGT_FUSED_GATHER=1, one scene, symmetric memory available), else None."""
+    """FusedKVGather when it applies (symmetric memory available, not disabled with IGGT_FUSED_GATHER=0), else None -
+    the caller then uses the NCCL all-gather."""
     import os
-    if os.environ.get("IGGT_FUSED_GATHER", "0") != "1" or B != 1 or world < 2:
+    import warnings
+    if os.environ.get("IGGT_FUSED_GATHER", "1") == "0" or world < 2 or _FUSED_FAILED or not torch.cuda.is_available():
         return None
-    key = (id(group), world, rank, S_loc, T, dtype, str(device))
+    key = (id(group), world, rank, B, S_loc, T, dtype, str(device))
     if key not in _FUSED:
-        _FUSED[key] = FusedKVGather(group, world, rank, S_loc, T, dtype, device)
+        try:
+            _FUSED[key] = FusedKVGather(group, world, rank, B, S_loc, T, dtype, device)
+        except Exception as e:     # no symmetric memory on this system / build: keep the collective
+            _FUSED_FAILED.append(repr(e))
+            warnings.warn(f"fused K|V gather unavailable ({e!r}); using the NCCL all-gather")
+            return None
     g = _FUSED[key]
     g.parity = 0
     return g

@@ -50,20 +50,22 @@ int iggt_gemm_store32(const void* A, int64_t lda, const void* W, int64_t ldw, fl
  * LayerNorm(64, eps 1e-5, affine) followed by 2-D RoPE (first 32 dims by y, last 32 by x, rotate-half
  * of 16, table [npos][16]).  Row r is token r % T of its view; pos_yx[T][2] holds (y,x).
  * Replaces iggt/layers/attention.py:52-58 + iggt/layers/rope.py:154-188.
- * gather_maps / n_gather (may be NULL / 0): see iggt_kv_gather_maps - the K | V chunks are also stored to every
+ * gather_maps / n_gather / gather_rows (may be NULL / 0 / 0): see iggt_kv_gather_maps - the K | V chunks are also stored to every
  * rank's gathered buffer (the all-gather of view sharding fused into this GEMM). */
 int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int64_t ldo,
                   int M, int C, int K, int dtype, const float* bias, int qk_norm,
                   const float* qn_w, const float* qn_b, const float* kn_w, const float* kn_b,
                   const float* rope_cos, const float* rope_sin, const int* pos_yx, int T,
-                  const void* gather_maps, int n_gather, iggt_stream_t stream);
+                  const void* gather_maps, int n_gather, int gather_rows, iggt_stream_t stream);
 
 /* View sharding (new design): n tensor maps (written to the device array dev_maps, 128 B each) through
- * which iggt_gemm_qkv (gather_maps / n_gather) stores the K | V chunks of every tile into each rank's gathered K|V
- * buffer as well - dst[i] = this rank's row window [rows, cols] (pitch ld) of rank i's buffer, a peer-mapped pointer
- * (torch symmetric memory over NVLink).  The collective it replaces: one all-gather of K|V per global block
- * (reference shape: iggt/models/aggregator.py:308-336, attention over all S*T keys). */
-int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int dtype, void* dev_maps);
+ * which iggt_gemm_qkv (gather_maps / n_gather / gather_rows = rows) stores the K | V chunks of every tile into each
+ * rank's gathered K|V buffer as well - dst[i] = this rank's first row inside rank i's buffer ([scenes][world*rows][cols],
+ * row pitch ld, scene pitch scene_ld elements), a peer-mapped pointer (torch symmetric memory over NVLink).  The
+ * collective it replaces: one all-gather of K|V per global block (reference shape: iggt/models/aggregator.py:308-336,
+ * attention over all S*T keys of a scene). */
+int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int64_t scenes, int64_t scene_ld,
+                        int dtype, void* dev_maps);
 
 /* 3x3 (pad 1, stride 1) or 1x1 convolution as implicit GEMM over an NHWC 16-bit tensor:
  * out[NB,H,W,Cout] = act_post(act(conv(x[NB,H,W,Cin], Wp[Cout, taps*Cin]) + bias) + resid + resid2)
