@@ -12,11 +12,12 @@
 //   * activations are tiny and live in L2: after each barrier the 8 consumer warps pull the phase's input rows
 //     ([M, <= 2048] fp32, 16-byte vectors) into shared memory, applying the LayerNorm that precedes the Linear on the way
 //     (statistics over the row, two-pass in registers);
-//   * every weight and every activation element is read from shared memory ONCE per tile: warp w owns a 32-wide k slice of
-//     each 256-wide stage, a lane owns one row and 8 (16) consecutive k of that slice and accumulates all 16 columns
-//     (packed FFMA2 over k pairs); partial sums meet through two shuffle rounds and an 8 KB shared-memory reduction.
-//     (A first version gave each warp 2 columns and made all 8 warps re-read the activations: 64 KB of shared-memory
-//     reads per 8 KB of weights - the timeline showed 1.3 TB/s of weight streaming.)
+//   * thread tile = 4 columns x M/2 rows x 8 k (warp = column group x row group, lane = k group of the 256-wide stage):
+//     32 fp16 -> fp32 conversions and 6 KB of shared-memory reads per warp and stage for 64 packed FFMA2 per thread, one
+//     butterfly over the lanes per tile.  (Timelines of the first two mappings, profiles/r02d / r02e_camera_*: "warp = 2
+//     columns, all rows" re-read the activations 8x from shared memory, "lane = row, all 16 columns" converted every
+//     weight 8x - 1.3 and 1.8 TB/s of weight streaming.)  LayerNorm gamma | beta are prefetched into shared memory by
+//     the producer like the weights (2-slot ring), so staging never waits on them;
 //   * bias, exact-erf GELU / SiLU, LayerScale, residual and the pose accumulation + activation ride in the epilogue;
 //   * the S x S attention (16 heads x 128) is a phase of its own: one warp per (row, head).
 // fp32 activations and accumulation, 16-bit weights - the arithmetic of iggt_skinny_gemm / iggt_small_attention, which
@@ -36,8 +37,8 @@ constexpr int CAM_KC = 256;                   // k per weight stage
 constexpr int CAM_STAGES = 8;
 constexpr int CAM_W_BYTES = CAM_COLS * CAM_KC * 2;       // 8 KB
 constexpr int CAM_X_FLOATS = 16384;           // activation buffer: [k][Mpad] fp32, 64 KB
-constexpr int CAM_RED_FLOATS = 8 * 16 * CAM_COLS;         // cross-warp reduction buffer [8 warps][<= 16 rows][16 cols]
-constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + CAM_RED_FLOATS * 4 + 256;
+constexpr int CAM_LN_FLOATS = 2 * 2 * CAM_DIM;            // LayerNorm gamma | beta of the next two LN phases (32 KB)
+constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + CAM_LN_FLOATS * 4 + 256;
 constexpr int CAM_MAX_PHASES = 32, CAM_MAX_MAPS = 24;
 
 enum CamPhaseType : int { PH_GEMM = 0, PH_ATTN = 1, PH_MODULATE = 2, PH_LNROWS = 3 };
@@ -118,15 +119,18 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
   extern __shared__ __align__(128) uint8_t cam_smem[];
   uint8_t* sW = cam_smem;
   float* xs = reinterpret_cast<float*>(cam_smem + CAM_STAGES * CAM_W_BYTES);
-  float* red = xs + CAM_X_FLOATS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + (CAM_X_FLOATS + CAM_RED_FLOATS) * 4);
+  float* lnbuf = xs + CAM_X_FLOATS;                       // [2 slots][gamma | beta][2048]
+  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + (CAM_X_FLOATS + CAM_LN_FLOATS) * 4);
   uint64_t* empty = full + CAM_STAGES;
+  uint64_t* ln_full = empty + CAM_STAGES;                 // [2]
+  uint64_t* ln_empty = ln_full + 2;                       // [2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int M = prog.M;
   constexpr int KX = CAM_X_FLOATS / MP;          // k extent of the activation buffer (2048 / 1024)
   if (threadIdx.x == 0) {
     for (int i = 0; i < CAM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ln_full[i], 1); mbar_init(&ln_empty[i], 8); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -137,12 +141,20 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
     // ------------------------------------------------------------------ weight producer: runs ahead of the barriers
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
+      int lslot = 0; uint32_t lph = 0;
       for (int it = 0; it < prog.iters; ++it)
         for (int p = 0; p < prog.n_phases; ++p) {
           const CamPhase& P = prog.ph[p];
           if (P.type != PH_GEMM || ((P.flags & CF_ONCE) && it > 0)) continue;
           const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
           const int nkb = (P.K + CAM_KC - 1) / CAM_KC;
+          if (P.ln == 1 && cta < tiles) {                   // gamma / beta of this phase's LayerNorm, ahead of time
+            mbar_wait(&ln_empty[lslot], lph ^ 1);
+            mbar_expect_tx(&ln_full[lslot], 2 * CAM_DIM * 4);
+            tma_bulk_load_1d(lnbuf + lslot * 2 * CAM_DIM, P.ln_w, CAM_DIM * 4, &ln_full[lslot]);
+            tma_bulk_load_1d(lnbuf + lslot * 2 * CAM_DIM + CAM_DIM, P.ln_b, CAM_DIM * 4, &ln_full[lslot]);
+            if (++lslot == 2) { lslot = 0; lph ^= 1; }
+          }
           for (int t = cta; t < tiles; t += G)
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(&empty[st], ph ^ 1);
@@ -159,6 +171,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
   const int tid = threadIdx.x;                   // 0..255
   unsigned target = 0;
   int st = 0; uint32_t ph = 0;
+  int lslot = 0; uint32_t lph = 0;
   for (int it = 0; it < prog.iters; ++it)
     for (int p = 0; p < prog.n_phases; ++p) {
       const CamPhase& P = prog.ph[p];
@@ -169,25 +182,29 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
         const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
         const int nchunks = (P.K + KX - 1) / KX;                         // activation chunks of KX
         const bool embed0 = (P.flags & CF_EMBED_IN) && it == 0;
-        // lane = (row m, k group kq): warp w owns k in [32 w, 32 w + 32) of every 256-wide stage, split over KQ lane
-        // groups of KL consecutive k; every lane accumulates ALL 16 columns of the tile for its row.
-        constexpr int KQ = 32 / MP;                                       // 4 (MP = 8) or 2 (MP = 16)
-        constexpr int KL = 32 / KQ;                                       // 8 or 16 consecutive k per lane and stage
-        const int lm = lane % MP, kq = lane / MP;
+        // thread tile = 4 columns x TM rows x 8 k: warp = (column group cg, row group mg), lane = k group of the stage
+        // (32 lanes x 8 = the stage's 256 k).  Every weight is converted once per row group, an activation element is
+        // read by the 4 column-group warps of its row group, and the k reduction is one butterfly per tile.
+        constexpr int TM = MP / 2;
+        const int cg = warp & 3, mg = warp >> 2;
+        const float* gam = lnbuf + lslot * 2 * CAM_DIM;
+        if (P.ln == 1 && cta < tiles) mbar_wait(&ln_full[lslot], lph);    // gamma | beta are in shared memory
         for (int t = cta; t < tiles; t += G) {
-          float2 acc[CAM_COLS];                                           // (even k, odd k) partial sums per column
+          float2 acc[4][TM];                                              // (even k, odd k) partial sums
 #pragma unroll
-          for (int c = 0; c < CAM_COLS; ++c) acc[c] = make_float2(0.f, 0.f);
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int m = 0; m < TM; ++m) acc[c][m] = make_float2(0.f, 0.f);
           for (int ch = 0; ch < nchunks; ++ch) {
             const int k0 = ch * KX;
             const int kn = min(KX, ((P.K - k0 + CAM_KC - 1) / CAM_KC) * CAM_KC);   // staged k extent (multiple of 256)
             if (t == cta || nchunks > 1) {
-              // ---- stage the activations [M, kn] as [k / 8][row][8] (16-byte vectors in and out), LayerNorm on the way
+              // ---- stage the activations as [row][k] (16-byte vectors in and out), LayerNorm applied on the way
               named_bar_sync(2, 256);                                     // previous readers of xs are done
               for (int m = warp; m < MP; m += 8) {
+                float* dst = xs + m * KX;
                 if (m >= M) {
-                  for (int k = lane * 4; k < kn; k += 128)
-                    *reinterpret_cast<float4*>(xs + ((k >> 3) * MP + m) * 8 + (k & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = lane * 4; k < kn; k += 128) *reinterpret_cast<float4*>(dst + k) = make_float4(0.f, 0.f, 0.f, 0.f);
                   continue;
                 }
                 const float* row = embed0 ? P.x2 : P.x + m * P.ldx;
@@ -214,17 +231,15 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
                     float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd,
                                            (v[i].w - mean) * rstd);
                     if (P.ln == 1) {
-                      const float4 ww = *reinterpret_cast<const float4*>(P.ln_w + k), bb = *reinterpret_cast<const float4*>(P.ln_b + k);
+                      const float4 ww = *reinterpret_cast<const float4*>(gam + k), bb = *reinterpret_cast<const float4*>(gam + CAM_DIM + k);
                       y.x = y.x * ww.x + bb.x; y.y = y.y * ww.y + bb.y; y.z = y.z * ww.z + bb.z; y.w = y.w * ww.w + bb.w;
                     }
-                    const int kk = k - k0;
-                    *reinterpret_cast<float4*>(xs + ((kk >> 3) * MP + m) * 8 + (kk & 7)) = y;
+                    *reinterpret_cast<float4*>(dst + (k - k0)) = y;
                   }
                 } else {
-                  for (int k = lane * 4; k < kn; k += 128) {             // P.K is a multiple of 4 (16, 1024, 2048, 8192)
-                    const float4 y = (k0 + k < P.K) ? *reinterpret_cast<const float4*>(row + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(xs + ((k >> 3) * MP + m) * 8 + (k & 7)) = y;
-                  }
+                  for (int k = lane * 4; k < kn; k += 128)               // P.K is a multiple of 4 (16, 1024, 2048, 8192)
+                    *reinterpret_cast<float4*>(dst + k) = (k0 + k < P.K) ? *reinterpret_cast<const float4*>(row + k0 + k)
+                                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
               }
               named_bar_sync(2, 256);
@@ -233,23 +248,28 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             // ---- weight stages of this chunk
             for (int kb = 0; kb < kn / CAM_KC; ++kb) {
               mbar_wait(&full[st], ph);
-              const int kl = warp * 32 + kq * KL;                         // first k of this lane inside the stage
-              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + kl;
-              const float* xk = xs + (((kb * CAM_KC + kl) >> 3) * MP + lm) * 8;
+              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (cg * 4) * CAM_KC + lane * 8;
+              const float* xk = xs + (mg * TM) * KX + kb * CAM_KC + lane * 8;
+              float2 wp[4][4];                                            // this thread's 4 columns x 8 k, as k pairs
 #pragma unroll
-              for (int g8 = 0; g8 < KL / 8; ++g8) {                       // 8 k at a time
-                const float4 xa = *reinterpret_cast<const float4*>(xk + g8 * MP * 8);
-                const float4 xb = *reinterpret_cast<const float4*>(xk + g8 * MP * 8 + 4);
+              for (int c = 0; c < 4; ++c) {
+                float wf[8];
+                cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + c * CAM_KC), wf);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wp[c][j] = make_float2(wf[2 * j], wf[2 * j + 1]);
+              }
+#pragma unroll
+              for (int m = 0; m < TM; ++m) {
+                const float4 xa = *reinterpret_cast<const float4*>(xk + m * KX);
+                const float4 xb = *reinterpret_cast<const float4*>(xk + m * KX + 4);
                 const float2 x01 = make_float2(xa.x, xa.y), x23 = make_float2(xa.z, xa.w);
                 const float2 x45 = make_float2(xb.x, xb.y), x67 = make_float2(xb.z, xb.w);
 #pragma unroll
-                for (int c = 0; c < CAM_COLS; ++c) {
-                  float wf[8];
-                  cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + c * CAM_KC + g8 * 8), wf);
-                  acc[c] = ffma2(make_float2(wf[0], wf[1]), x01, acc[c]);
-                  acc[c] = ffma2(make_float2(wf[2], wf[3]), x23, acc[c]);
-                  acc[c] = ffma2(make_float2(wf[4], wf[5]), x45, acc[c]);
-                  acc[c] = ffma2(make_float2(wf[6], wf[7]), x67, acc[c]);
+                for (int c = 0; c < 4; ++c) {
+                  acc[c][m] = ffma2(wp[c][0], x01, acc[c][m]);
+                  acc[c][m] = ffma2(wp[c][1], x23, acc[c][m]);
+                  acc[c][m] = ffma2(wp[c][2], x45, acc[c][m]);
+                  acc[c][m] = ffma2(wp[c][3], x67, acc[c][m]);
                 }
               }
               __syncwarp();
@@ -257,28 +277,18 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
           }
-          // ---- reduce: lanes of a row over their k groups (shuffles), then the 8 warps' k slices through shared memory
-          float part[CAM_COLS];
+          // ---- reduce over the lanes' k groups; lane (c * TM + m) keeps column c, row m of the warp's tile
+          float mine = 0.f;
 #pragma unroll
-          for (int c = 0; c < CAM_COLS; ++c) {
-            float v = acc[c].x + acc[c].y;
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int o = MP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            part[c] = v;
-          }
-          named_bar_sync(2, 256);                                         // the previous tile's sums have been read
-          if (kq == 0) {
-#pragma unroll
-            for (int c = 0; c < CAM_COLS; c += 4)
-              *reinterpret_cast<float4*>(red + (warp * MP + lm) * CAM_COLS + c) = make_float4(part[c], part[c + 1], part[c + 2], part[c + 3]);
-          }
-          named_bar_sync(2, 256);
-          if (tid < MP * CAM_COLS) {
-            const int m = tid / CAM_COLS, c = tid % CAM_COLS;
-            float mine = 0.f;
-#pragma unroll
-            for (int wv = 0; wv < 8; ++wv) mine += red[(wv * MP + m) * CAM_COLS + c];
-            const int n = t * CAM_COLS + c;
+            for (int m = 0; m < TM; ++m) {
+              const float v = warp_sum_f(acc[c][m].x + acc[c][m].y);
+              if (lane == c * TM + m) mine = v;
+            }
+          if (lane < 4 * TM) {
+            const int c = lane / TM, m = mg * TM + lane % TM;
+            const int n = t * CAM_COLS + cg * 4 + c;
             if (n < P.N && m < M) {
               float v = mine + (P.bias ? P.bias[n] : 0.f);
               if (P.act == 1) v = gelu_erf(v);
@@ -293,6 +303,11 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               P.out[m * P.ldo + n] = v;
             }
           }
+        }
+        if (P.ln == 1 && cta < tiles) {                                   // release the gamma | beta slot
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ln_empty[lslot]);
+          if (++lslot == 2) { lslot = 0; lph ^= 1; }
         }
       } else if (P.type == PH_ATTN) {
         // one warp per (row, head): q . k_j over the S tokens of the row's scene, softmax, p . v
