@@ -284,8 +284,8 @@ def run_b200(args):
         peak_exp = 16.0 * 148 * clk * 1e6
         roof["mufu_roofline"] = {"achieved_gexp_s": exps / (d["ms"] * 1e-3) / 1e9, "peak_gexp_s": peak_exp / 1e9,
                                  "frac": exps / (d["ms"] * 1e-3) / peak_exp,
-                                 "note": "ncu (profiles/r01final_ncu_attention3_kernel_*.csv): sm__inst_executed_pipe_xu 75.3 % (global), 54.2 % (frame) of peak"}
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+                                 "note": "ncu (profiles/r02a_ncu_all_kernels.csv): sm__inst_executed_pipe_xu 75.7 % (global), 55.1 % (frame) of peak; the softmax warps are latency-bound, not MUFU-bound (profiles/r02b_attn_sweep.json)"}
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         if os.path.exists(tp) and world == 1 and args.views == 8 and args.size == 518:
             t = json.load(open(tp))["iggt_attention_fwd"]
             # per launch, averaged over the 24 global + 48 frame launches of a step

@@ -107,6 +107,16 @@ __device__ __forceinline__ void cam_unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
+// k-block actually processed at step `kb` of a tile: rotated by the CTA index inside its activation chunk (kpc k-blocks).
+// All CTAs walk the weight rows in lock step; without the rotation they all read the same 512-byte column window of rows
+// that are a power-of-two pitch (4 / 16 KB) apart at the same time, which camps on a few HBM channels (the stream sat at
+// 1.8 TB/s whatever the thread mapping or ring depth, profiles/r02f / r02g_camera_*).
+__device__ __forceinline__ int cam_rot(int kb, int nkb, int kpc, int cta) {
+  const int base = (kb / kpc) * kpc;
+  const int n = min(kpc, nkb - base);
+  return base + (kb - base + cta) % n;
+}
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -160,7 +170,8 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(&empty[st], ph ^ 1);
               mbar_expect_tx(&full[st], CAM_W_BYTES);
-              tma_load_2d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], kb * CAM_KC, t * CAM_COLS);
+              tma_load_2d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], cam_rot(kb, nkb, KX / CAM_KC, cta) * CAM_KC,
+                          t * CAM_COLS);
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
         }
@@ -250,7 +261,8 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             for (int kb = 0; kb < kn / CAM_KC; ++kb) {
               mbar_wait(&full[st], ph);
               const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (cg * 4) * CAM_KC + lane * 8;
-              const float* xk = xs + (mg * TM) * KX + kb * CAM_KC + lane * 8;
+              const int kr = cam_rot(kb, kn / CAM_KC, KX / CAM_KC, cta);       // the producer's order (chunk-local here)
+              const float* xk = xs + (mg * TM) * KX + kr * CAM_KC + lane * 8;
               float2 wp[4][4];                                            // this thread's 4 columns x 8 k, as k pairs
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
