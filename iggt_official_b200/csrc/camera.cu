@@ -66,6 +66,7 @@ struct CamProgram {
   int n_phases, iters, M, Mpad, B, S;
   unsigned* barrier;           // zeroed before the launch
   unsigned long long* dbg;     // optional (IGGT_CAMERA_DEBUG=1): CTA 0 stamps %globaltimer at 4 points of every phase
+  int dbg_mode;                // 2: consumers skip the arithmetic (pure weight-streaming rate; results are garbage)
 };
 
 __device__ __forceinline__ unsigned long long cam_now() {
@@ -189,6 +190,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
       const CamPhase& P = prog.ph[p];
       if ((P.flags & CF_ONCE) && it > 0) continue;
       unsigned long long* stamp = (prog.dbg && cta == 0 && tid == 0) ? prog.dbg + (it * CAM_MAX_PHASES + p) * 4 : nullptr;
+      long long wait_clk = 0;
       if (stamp) stamp[0] = cam_now();
       if (P.type == PH_GEMM) {
         const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
@@ -259,7 +261,15 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             }
             // ---- weight stages of this chunk
             for (int kb = 0; kb < kn / CAM_KC; ++kb) {
+              const long long tw0 = stamp ? clock64() : 0;
               mbar_wait(&full[st], ph);
+              if (stamp) wait_clk += clock64() - tw0;
+              if (prog.dbg_mode == 2) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
+                continue;
+              }
               const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (cg * 4) * CAM_KC + lane * 8;
               const int kr = cam_rot(kb, kn / CAM_KC, KX / CAM_KC, cta);       // the producer's order (chunk-local here)
               const float* xk = xs + (mg * TM) * KX + kr * CAM_KC + lane * 8;
@@ -392,7 +402,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
       }
       if (stamp) stamp[2] = cam_now();
       cam_grid_sync(prog.barrier, target);
-      if (stamp) stamp[3] = cam_now();
+      if (stamp) stamp[3] = cam_now() | (static_cast<unsigned long long>(wait_clk >> 6) << 48);   // + cycles/64 spent waiting for weights
     }
 }
 
@@ -444,6 +454,7 @@ extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* token
   CamProgram prog{};
   prog.iters = iters; prog.M = M; prog.Mpad = M <= 8 ? 8 : 16; prog.B = B; prog.S = S; prog.barrier = ws.barrier;
   prog.dbg = (dbg_env && iters <= 8) ? reinterpret_cast<unsigned long long*>(ws.barrier + 32) : nullptr;   // +128 B
+  prog.dbg_mode = dbg_env;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   int nmaps = 0;
   auto add_map = [&](const void* W, int N, int K) -> int {

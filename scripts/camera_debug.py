@@ -30,12 +30,16 @@ M = B * S
 floats = M * (5 * 2048 + 2 * 3 * 2048 + 4 * 2048 + 1024 + 16)
 off = (floats * 4 + 127) // 128 * 128 + 128
 dbg = ws[off:off + 8 * 32 * 4 * 8].view(torch.int64).view(8, 32, 4).cpu()
-t0 = int(dbg[0, 0, 0])
+t0 = int(dbg[0, 0, 0]) & ((1 << 48) - 1)
 names = ["ln_tok", "ln_adaln", "embed", "mod", "modulate"] + [f"b{b}.{n}" for b in range(4) for n in ("qkv", "attn", "proj", "fc1", "fc2")] + ["pb1", "pb2"]
 tot = {"stage": 0.0, "work": 0.0, "barrier": 0.0}
 for i in range(it):
     for p, name in enumerate(names):
         a, b, c, d = [int(x) for x in dbg[i, p]]
+        wait_cyc = ((d >> 48) & 0xFFFF) * 64
+        d &= (1 << 48) - 1
+        a48, b48, c48 = a & ((1 << 48) - 1), b & ((1 << 48) - 1), c & ((1 << 48) - 1)
+        a, b, c = a48, (b48 if b else 0), c48
         if a == 0:
             continue
         stage = (b - a) / 1e3 if b else 0.0
@@ -43,5 +47,5 @@ for i in range(it):
         bar = (d - c) / 1e3
         tot["stage"] += stage; tot["work"] += work; tot["barrier"] += bar
         if i == 1:
-            print(f"iter {i} {name:10s} start {(a - t0) / 1e3:8.1f} us  stage {stage:6.1f}  work {work:6.1f}  barrier {bar:6.1f}")
+            print(f"iter {i} {name:10s} start {(a - t0) / 1e3:8.1f} us  stage {stage:6.1f}  work {work:6.1f}  barrier {bar:6.1f}  waiting-for-weights {wait_cyc} cycles")
 print({k: round(v, 1) for k, v in tot.items()}, "us total over", it, "iterations (CTA 0's view)")
