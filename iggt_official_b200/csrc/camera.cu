@@ -6,22 +6,24 @@
 // latency-bound: 2.0 ms of the 54 ms C2 step on one GPU and 12 % of the step on each of 8 view-sharded ranks, where the
 // head is replicated.  Here the ~27 phases of an iteration run inside one grid of <= 128 CTAs with a device-wide barrier
 // between phases:
-//   * warp 8 is a TMA producer that walks the same phase program AHEAD of the consumers: weight tiles
-//     ({256 k, 16 columns}, 8 KB) of the next phases stream into an 8-stage ring while the consumers are still in the
-//     barrier of the current one - weights do not depend on activations - so HBM stays busy across phase boundaries;
+//   * warp 8 is a TMA producer that walks the same phase program AHEAD of the consumers: weight stages (ONE 3-D box
+//     {64 k, 16 columns, 16 k groups} = 1024 k x 16 columns = 32 KB per instruction, 128B-swizzled) of the next phases
+//     stream into a 3-stage ring while the consumers are still in the barrier of the current one - weights do not depend on
+//     activations - so HBM stays busy across phase boundaries; LayerNorm gamma | beta come through a 2-slot bulk-copy ring;
 //   * activations are tiny and live in L2: after each barrier the 8 consumer warps pull the phase's input rows
-//     ([M, <= 2048] fp32, 16-byte vectors) into shared memory, applying the LayerNorm that precedes the Linear on the way
-//     (statistics over the row, two-pass in registers);
-//   * thread tile = 4 columns x M/2 rows x 8 k (warp = column group x row group, lane = k group of the 256-wide stage):
-//     32 fp16 -> fp32 conversions and 6 KB of shared-memory reads per warp and stage for 64 packed FFMA2 per thread, one
-//     butterfly over the lanes per tile.  (Timelines of the first two mappings, profiles/r02d / r02e_camera_*: "warp = 2
-//     columns, all rows" re-read the activations 8x from shared memory, "lane = row, all 16 columns" converted every
-//     weight 8x - 1.3 and 1.8 TB/s of weight streaming.)  LayerNorm gamma | beta are prefetched into shared memory by
-//     the producer like the weights (2-slot ring), so staging never waits on them;
+//     ([M, <= 2048] fp32, 16-byte vectors), apply the LayerNorm that precedes the Linear (statistics over the row, two-pass
+//     in registers) and store them as TWO 16-bit planes hi + lo = x (cam_split);
+//   * the products run on the tensor cores (mma.sync.m16n8k16, fp32 accumulate): C[16 x 16] += (X_hi + X_lo) W^T, warp w
+//     takes every 8th k step of a stage, fragments come straight from the swizzled stage / the padded planes (bank-conflict
+//     free), the 8 warps' partial tiles meet in an 8 KB shared-memory reduction and thread (row, column) finishes one output.
+//     History (timelines under profiles/r02*_camera_*): three CUDA-core thread mappings all sat at 1.6-1.8 TB/s of weight
+//     streaming - the fp32 pipe (FFMA2 at one per 4 clk per scheduler) was the limit, and with the arithmetic removed the
+//     stream itself topped out at 3.0 TB/s because one thread issued one 8 KB TMA box at a time;
 //   * bias, exact-erf GELU / SiLU, LayerScale, residual and the pose accumulation + activation ride in the epilogue;
 //   * the S x S attention (16 heads x 128) is a phase of its own: one warp per (row, head).
-// fp32 activations and accumulation, 16-bit weights - the arithmetic of iggt_skinny_gemm / iggt_small_attention, which
-// this kernel replaces for M <= 16 (larger B*S keep the per-layer launches).
+// fp32 accumulation, 16-bit weights, activations to ~2^-22 (fp16 weights) / 2^-16 (bf16) relative - within rounding of the
+// arithmetic of iggt_skinny_gemm / iggt_small_attention, which this kernel replaces for M <= 16 (larger B*S keep the
+// per-layer launches).
 #include <stdlib.h>
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -32,13 +34,14 @@ namespace iggt {
 
 constexpr int CAM_DIM = 2048, CAM_HEADS = 16, CAM_HD = 128;
 constexpr int CAM_THREADS = 288;              // 8 consumer warps + 1 producer warp
-constexpr int CAM_COLS = 16;                  // output columns per tile
-constexpr int CAM_KC = 256;                   // k per weight stage
-constexpr int CAM_STAGES = 16;             // 128 KB of weights in flight per SM: at 8 stages the stream sat at 1.8 TB/s (latency x concurrency)
-constexpr int CAM_W_BYTES = CAM_COLS * CAM_KC * 2;       // 8 KB
-constexpr int CAM_X_FLOATS = 16384;           // activation buffer: [k][Mpad] fp32, 64 KB
-constexpr int CAM_LN_FLOATS = 2 * 2 * CAM_DIM;            // LayerNorm gamma | beta of the next two LN phases (32 KB)
-constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_FLOATS * 4 + CAM_LN_FLOATS * 4 + 512;   // + 36 mbarriers
+constexpr int CAM_COLS = 16;                  // output columns per tile (two n-tiles of mma.m16n8k16)
+constexpr int CAM_KS = 1024;                  // k per weight stage: ONE 3-D TMA box {64 k, 16 columns, 16 k groups} = 32 KB
+constexpr int CAM_STAGES = 3;
+constexpr int CAM_W_BYTES = CAM_COLS * CAM_KS * 2;       // 32 KB
+constexpr int CAM_X_BYTES = 2 * 16 * (1024 + 8) * 2;     // activation planes (hi | lo) [rows][KX + 8] 16-bit: 8 x 2056 or 16 x 1032 per plane
+constexpr int CAM_LN_FLOATS = 2 * 2 * CAM_DIM;           // LayerNorm gamma | beta of the next two LN phases (32 KB)
+constexpr int CAM_RED_FLOATS = 8 * 16 * CAM_COLS;        // cross-warp reduction [8 warps][16 rows][16 cols] (8 KB)
+constexpr int CAM_SMEM = CAM_STAGES * CAM_W_BYTES + CAM_X_BYTES + CAM_LN_FLOATS * 4 + CAM_RED_FLOATS * 4 + 512;
 static_assert(CAM_SMEM <= 232448, "shared memory budget");
 constexpr int CAM_MAX_PHASES = 32, CAM_MAX_MAPS = 24;
 
@@ -92,30 +95,29 @@ __device__ __forceinline__ void cam_grid_sync(unsigned* counter, unsigned& targe
   named_bar_sync(1, 256);
 }
 
+// D (16 x 8, fp32) += A (16 x 16, row) * B (16 x 8, col), 16-bit operands
 template <bool BF16>
-__device__ __forceinline__ void cam_unpack8(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if constexpr (BF16) {
-      f[2 * j] = __uint_as_float(w[j] << 16);
-      f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
-    } else {
-      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
-      f[2 * j] = __low2float(h);
-      f[2 * j + 1] = __high2float(h);
-    }
-  }
+__device__ __forceinline__ void cam_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-
-// k-block actually processed at step `kb` of a tile: rotated by the CTA index inside its activation chunk (kpc k-blocks).
-// All CTAs walk the weight rows in lock step; without the rotation they all read the same 512-byte column window of rows
-// that are a power-of-two pitch (4 / 16 KB) apart at the same time, which camps on a few HBM channels (the stream sat at
-// 1.8 TB/s whatever the thread mapping or ring depth, profiles/r02f / r02g_camera_*).
-__device__ __forceinline__ int cam_rot(int kb, int nkb, int kpc, int cta) {
-  const int base = (kb / kpc) * kpc;
-  const int n = min(kpc, nkb - base);
-  return base + (kb - base + cta) % n;
+// x = hi + lo with hi, lo in the weights' 16-bit type: the fp32 activation enters the tensor cores as two operands
+// (products with the 16-bit weights are exact in fp32, so the split only costs the ~2^-22 (fp16) / 2^-16 (bf16) of x it drops)
+template <bool BF16>
+__device__ __forceinline__ void cam_split(float x, uint16_t& hi, uint16_t& lo) {
+  if constexpr (BF16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h); lo = *reinterpret_cast<const uint16_t*>(&l);
+  } else {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h); lo = *reinterpret_cast<const uint16_t*>(&l);
+  }
 }
 
 __device__ __forceinline__ float warp_sum_f(float v) {
@@ -128,18 +130,21 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 template <bool BF16, int MP>
 __global__ void __launch_bounds__(CAM_THREADS, 1)
 camera_head_kernel(const __grid_constant__ CamProgram prog) {
-  extern __shared__ __align__(128) uint8_t cam_smem[];
+  extern __shared__ __align__(1024) uint8_t cam_smem[];      // 128B-swizzled weight stages need 1024-byte alignment
   uint8_t* sW = cam_smem;
-  float* xs = reinterpret_cast<float*>(cam_smem + CAM_STAGES * CAM_W_BYTES);
-  float* lnbuf = xs + CAM_X_FLOATS;                       // [2 slots][gamma | beta][2048]
-  uint64_t* full = reinterpret_cast<uint64_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES + (CAM_X_FLOATS + CAM_LN_FLOATS) * 4);
+  uint16_t* xs = reinterpret_cast<uint16_t*>(cam_smem + CAM_STAGES * CAM_W_BYTES);     // hi plane, then lo plane
+  float* lnbuf = reinterpret_cast<float*>(cam_smem + CAM_STAGES * CAM_W_BYTES + CAM_X_BYTES);     // [2 slots][gamma | beta][2048]
+  float* red = lnbuf + CAM_LN_FLOATS;                     // [8 warps][16 rows][16 cols]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + CAM_RED_FLOATS);
   uint64_t* empty = full + CAM_STAGES;
   uint64_t* ln_full = empty + CAM_STAGES;                 // [2]
   uint64_t* ln_empty = ln_full + 2;                       // [2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int M = prog.M;
-  constexpr int KX = CAM_X_FLOATS / MP;          // k extent of the activation buffer (2048 / 1024)
+  constexpr int KX = 16384 / MP;                 // k extent of the staged activations (2048 for <= 8 rows, 1024 for <= 16)
+  constexpr int KXP = KX + 8;                    // plane row pitch (16-bit elements): +16 B spreads the 8 rows of a fragment over all banks
+  uint16_t* const xlo = xs + MP * KXP;
   if (threadIdx.x == 0) {
     for (int i = 0; i < CAM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
     for (int i = 0; i < 2; ++i) { mbar_init(&ln_full[i], 1); mbar_init(&ln_empty[i], 8); }
@@ -159,7 +164,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
           const CamPhase& P = prog.ph[p];
           if (P.type != PH_GEMM || ((P.flags & CF_ONCE) && it > 0)) continue;
           const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
-          const int nkb = (P.K + CAM_KC - 1) / CAM_KC;
+          const int nst = (P.K + CAM_KS - 1) / CAM_KS;      // 32 KB stages per tile
           if (P.ln == 1 && cta < tiles) {                   // gamma / beta of this phase's LayerNorm, ahead of time
             mbar_wait(&ln_empty[lslot], lph ^ 1);
             mbar_expect_tx(&ln_full[lslot], 2 * CAM_DIM * 4);
@@ -168,11 +173,10 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             if (++lslot == 2) { lslot = 0; lph ^= 1; }
           }
           for (int t = cta; t < tiles; t += G)
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int ks = 0; ks < nst; ++ks) {
               mbar_wait(&empty[st], ph ^ 1);
-              mbar_expect_tx(&full[st], CAM_W_BYTES);
-              tma_load_2d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], cam_rot(kb, nkb, KX / CAM_KC, cta) * CAM_KC,
-                          t * CAM_COLS);
+              mbar_expect_tx(&full[st], CAM_W_BYTES);       // the box is always 32 KB (out-of-range k groups / columns: zeros)
+              tma_load_3d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], 0, t * CAM_COLS, ks * (CAM_KS / 64));
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
         }
@@ -196,32 +200,40 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
         const int tiles = (P.N + CAM_COLS - 1) / CAM_COLS;
         const int nchunks = (P.K + KX - 1) / KX;                         // activation chunks of KX
         const bool embed0 = (P.flags & CF_EMBED_IN) && it == 0;
-        // thread tile = 4 columns x TM rows x 8 k: warp = (column group cg, row group mg), lane = k group of the stage
-        // (32 lanes x 8 = the stage's 256 k).  Every weight is converted once per row group, an activation element is
-        // read by the 4 column-group warps of its row group, and the k reduction is one butterfly per tile.
-        constexpr int TM = MP / 2;
-        const int cg = warp & 3, mg = warp >> 2;
+        // Tensor-core math: C[16 rows x 16 cols] += X[16 x k] W^T with mma.m16n8k16; the fp32 activations enter as two 16-bit
+        // operands (hi + lo, cam_split), the weights straight from their 128B-swizzled TMA stage.  Warp w owns k steps
+        // [8 w', 8 w' + 8) of every 128-step stage quarter...: each stage of 1024 k = 64 k steps of 16, 8 per warp.
+        const int g = lane >> 2, tq = lane & 3;
         const float* gam = lnbuf + lslot * 2 * CAM_DIM;
         if (P.ln == 1 && cta < tiles) mbar_wait(&ln_full[lslot], lph);    // gamma | beta are in shared memory
         for (int t = cta; t < tiles; t += G) {
-          float2 acc[4][TM];                                              // (even k, odd k) partial sums
+          float acc[2][4];                                                // two n-tiles (8 columns each) x (rows g, g + 8)
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int m = 0; m < TM; ++m) acc[c][m] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
           for (int ch = 0; ch < nchunks; ++ch) {
             const int k0 = ch * KX;
-            const int kn = min(KX, ((P.K - k0 + CAM_KC - 1) / CAM_KC) * CAM_KC);   // staged k extent (multiple of 256)
+            const int kn = min(KX, P.K - k0);                             // k of this chunk (16, 1024, 2048)
+            const int kst = (kn + 15) & ~15;                              // staged extent: whole k steps
             if (t == cta || nchunks > 1) {
-              // ---- stage the activations as [row][k] (16-byte vectors in and out), LayerNorm applied on the way
+              // ---- stage the activations as 16-bit planes hi | lo, [row][KXP], LayerNorm applied on the way
               named_bar_sync(2, 256);                                     // previous readers of xs are done
               for (int m = warp; m < MP; m += 8) {
-                float* dst = xs + m * KX;
+                uint16_t* dh = xs + m * KXP;
+                uint16_t* dl = xlo + m * KXP;
                 if (m >= M) {
-                  for (int k = lane * 4; k < kn; k += 128) *reinterpret_cast<float4*>(dst + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = lane * 4; k < kst; k += 128) { *reinterpret_cast<uint2*>(dh + k) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(dl + k) = make_uint2(0u, 0u); }
                   continue;
                 }
                 const float* row = embed0 ? P.x2 : P.x + m * P.ldx;
+                auto put = [&](int k, const float4& y) {                  // 4 consecutive k -> 8 bytes in each plane
+                  uint16_t h[4], l[4];
+                  cam_split<BF16>(y.x, h[0], l[0]); cam_split<BF16>(y.y, h[1], l[1]);
+                  cam_split<BF16>(y.z, h[2], l[2]); cam_split<BF16>(y.w, h[3], l[3]);
+                  *reinterpret_cast<uint2*>(dh + k) = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
+                  *reinterpret_cast<uint2*>(dl + k) = make_uint2(l[0] | (static_cast<uint32_t>(l[1]) << 16), l[2] | (static_cast<uint32_t>(l[3]) << 16));
+                };
                 if (P.ln) {                                               // row length 2048; KX is 2048 or 1024
                   float4 v[CAM_DIM / 128];
                   float s = 0.f;
@@ -248,51 +260,47 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
                       const float4 ww = *reinterpret_cast<const float4*>(gam + k), bb = *reinterpret_cast<const float4*>(gam + CAM_DIM + k);
                       y.x = y.x * ww.x + bb.x; y.y = y.y * ww.y + bb.y; y.z = y.z * ww.z + bb.z; y.w = y.w * ww.w + bb.w;
                     }
-                    *reinterpret_cast<float4*>(dst + (k - k0)) = y;
+                    put(k - k0, y);
                   }
                 } else {
-                  for (int k = lane * 4; k < kn; k += 128)               // P.K is a multiple of 4 (16, 1024, 2048, 8192)
-                    *reinterpret_cast<float4*>(dst + k) = (k0 + k < P.K) ? *reinterpret_cast<const float4*>(row + k0 + k)
-                                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = lane * 4; k < kst; k += 128)              // P.K is a multiple of 4 (16, 1024, 2048, 8192)
+                    put(k, (k0 + k < P.K) ? *reinterpret_cast<const float4*>(row + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f));
                 }
               }
               named_bar_sync(2, 256);
               if (stamp && t == cta && ch == 0) stamp[1] = cam_now();
             }
-            // ---- weight stages of this chunk
-            for (int kb = 0; kb < kn / CAM_KC; ++kb) {
-              const long long tw0 = stamp ? clock64() : 0;
+            // ---- weight stages of this chunk (1024 k each)
+            for (int ks = 0; ks < (kn + CAM_KS - 1) / CAM_KS; ++ks) {
               mbar_wait(&full[st], ph);
-              if (stamp) wait_clk += clock64() - tw0;
-              if (prog.dbg_mode == 2) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
-                if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
-                continue;
-              }
-              const uint16_t* w = reinterpret_cast<const uint16_t*>(sW + st * CAM_W_BYTES) + (cg * 4) * CAM_KC + lane * 8;
-              const int kr = cam_rot(kb, kn / CAM_KC, KX / CAM_KC, cta);       // the producer's order (chunk-local here)
-              const float* xk = xs + (mg * TM) * KX + kr * CAM_KC + lane * 8;
-              float2 wp[4][4];                                            // this thread's 4 columns x 8 k, as k pairs
+              if (prog.dbg_mode != 2) {
+                const uint8_t* wst = sW + st * CAM_W_BYTES;
+                const int steps = min(CAM_KS, kn - ks * CAM_KS + 15) / 16;      // k steps of 16 in this stage (64, or 1 for K = 16)
+                for (int s16 = warp; s16 < steps; s16 += 8) {
+                  const int kk = ks * CAM_KS + s16 * 16;                  // chunk-local k of this step
+                  // A fragments: rows g (and g + 8 when more than 8 rows are staged), k = kk + 2 tq (+ 8)
+                  const uint32_t ah0 = *reinterpret_cast<const uint32_t*>(xs + g * KXP + kk + 2 * tq);
+                  const uint32_t ah2 = *reinterpret_cast<const uint32_t*>(xs + g * KXP + kk + 8 + 2 * tq);
+                  const uint32_t al0 = *reinterpret_cast<const uint32_t*>(xlo + g * KXP + kk + 2 * tq);
+                  const uint32_t al2 = *reinterpret_cast<const uint32_t*>(xlo + g * KXP + kk + 8 + 2 * tq);
+                  uint32_t ah1 = 0, ah3 = 0, al1 = 0, al3 = 0;
+                  if constexpr (MP == 16) {
+                    ah1 = *reinterpret_cast<const uint32_t*>(xs + (g + 8) * KXP + kk + 2 * tq);
+                    ah3 = *reinterpret_cast<const uint32_t*>(xs + (g + 8) * KXP + kk + 8 + 2 * tq);
+                    al1 = *reinterpret_cast<const uint32_t*>(xlo + (g + 8) * KXP + kk + 2 * tq);
+                    al3 = *reinterpret_cast<const uint32_t*>(xlo + (g + 8) * KXP + kk + 8 + 2 * tq);
+                  }
+                  // B fragments from the swizzled stage: k group (64 k) q64, 16-byte chunk (2 j) ^ (col & 7), + 4 tq bytes
+                  const int q64 = s16 >> 2, j = (s16 & 3) * 2;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float wf[8];
-                cam_unpack8<BF16>(*reinterpret_cast<const uint4*>(w + c * CAM_KC), wf);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wp[c][j] = make_float2(wf[2 * j], wf[2 * j + 1]);
-              }
-#pragma unroll
-              for (int m = 0; m < TM; ++m) {
-                const float4 xa = *reinterpret_cast<const float4*>(xk + m * KX);
-                const float4 xb = *reinterpret_cast<const float4*>(xk + m * KX + 4);
-                const float2 x01 = make_float2(xa.x, xa.y), x23 = make_float2(xa.z, xa.w);
-                const float2 x45 = make_float2(xb.x, xb.y), x67 = make_float2(xb.z, xb.w);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  acc[c][m] = ffma2(wp[c][0], x01, acc[c][m]);
-                  acc[c][m] = ffma2(wp[c][1], x23, acc[c][m]);
-                  acc[c][m] = ffma2(wp[c][2], x45, acc[c][m]);
-                  acc[c][m] = ffma2(wp[c][3], x67, acc[c][m]);
+                  for (int c = 0; c < 2; ++c) {
+                    const int col = c * 8 + g;
+                    const uint8_t* wr = wst + q64 * (CAM_COLS * 128) + col * 128 + tq * 4;
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr + ((j ^ (col & 7)) << 4));
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + (((j + 1) ^ (col & 7)) << 4));
+                    cam_mma<BF16>(acc[c], ah0, ah1, ah2, ah3, b0, b1);
+                    cam_mma<BF16>(acc[c], al0, al1, al2, al3, b0, b1);
+                  }
                 }
               }
               __syncwarp();
@@ -300,18 +308,21 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
           }
-          // ---- reduce over the lanes' k groups; lane (c * TM + m) keeps column c, row m of the warp's tile
-          float mine = 0.f;
+          // ---- reduce the 8 warps' k slices through shared memory; thread (m, c) finishes one output element
+          named_bar_sync(2, 256);                                         // the previous tile's sums have been read
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c) {
+            float* r0 = red + (warp * 16 + g) * CAM_COLS + c * 8 + 2 * tq;
+            *reinterpret_cast<float2*>(r0) = make_float2(acc[c][0], acc[c][1]);
+            *reinterpret_cast<float2*>(r0 + 8 * CAM_COLS) = make_float2(acc[c][2], acc[c][3]);
+          }
+          named_bar_sync(2, 256);
+          {
+            const int m = tid / CAM_COLS, c = tid % CAM_COLS;
+            float mine = 0.f;
 #pragma unroll
-            for (int m = 0; m < TM; ++m) {
-              const float v = warp_sum_f(acc[c][m].x + acc[c][m].y);
-              if (lane == c * TM + m) mine = v;
-            }
-          if (lane < 4 * TM) {
-            const int c = lane / TM, m = mg * TM + lane % TM;
-            const int n = t * CAM_COLS + cg * 4 + c;
+            for (int wv = 0; wv < 8; ++wv) mine += red[(wv * 16 + m) * CAM_COLS + c];
+            const int n = t * CAM_COLS + c;
             if (n < P.N && m < M) {
               float v = mine + (P.bias ? P.bias[n] : 0.f);
               if (P.act == 1) v = gelu_erf(v);
@@ -457,11 +468,13 @@ extern "C" int iggt_camera_head(const iggt_camera_weights* w, const float* token
   prog.dbg_mode = dbg_env;
   const TmDtype dt = dtype ? TM_BF16 : TM_F16;
   int nmaps = 0;
+  // weights [N, K] row-major seen as {64 k, N, K / 64} (128B-swizzled rows of 64 k): one box = 16 columns x 1024 k
   auto add_map = [&](const void* W, int N, int K) -> int {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
-    uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {(uint32_t)CAM_KC, (uint32_t)CAM_COLS};
-    if (nmaps >= CAM_MAX_MAPS || make_tmap(&prog.maps[nmaps], dt, 2, W, dims, str, box, false)) return -1;
+    const int k64 = K < 64 ? K : 64;                       // embed_pose: K = 16
+    uint64_t dims[3] = {(uint64_t)k64, (uint64_t)N, (uint64_t)((K + 63) / 64)};
+    uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)128};
+    uint32_t box[3] = {64, (uint32_t)CAM_COLS, (uint32_t)(CAM_KS / 64)};
+    if (nmaps >= CAM_MAX_MAPS || make_tmap(&prog.maps[nmaps], dt, 3, W, dims, str, box, true)) return -1;
     return nmaps++;
   };
   int np = 0;

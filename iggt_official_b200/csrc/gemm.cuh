@@ -58,8 +58,10 @@ struct GemmParams {
   // K|V buffer, reached over NVLink peer mappings): the all-gather of the global attention's keys and values is fused
   // into the producing GEMM, tile by tile (parallel.py, FusedKVGather)
   // The maps are 3-D {2048 columns, rows of one scene, scenes}: the rank's rows (scene, view, token) land at
-  // (scene, rank, view, token) in the gathered buffer; a 128-row tile that straddles two scenes is stored twice, the
-  // second time with a negative row origin in the next scene (TMA clips both stores to their scene).
+  // (scene, rank, view, token) in the gathered buffer.  The TMA store of a 128-row tile is clipped to the scene of the
+  // tile's first row; rows of a tile that belong to a later scene (B - 1 tiles per GEMM) are written by their epilogue
+  // threads with plain 16-byte stores through the raw peer pointers that follow the maps in the device array
+  // ([n maps][n pointers][ld, scene_ld as int64]).
   const CUtensorMap* gather_maps;
   int n_gather;
   int gather_col0;
@@ -479,6 +481,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           // registers -> 128B-swizzled staging tile (row = 128 B = 64 x 16 bit)
+          bool later_scene = false;                                       // EPI_QKV gather: this row is not in the tile's first scene
+          if constexpr (EPI == EPI_QKV) {
+            if (p.n_gather > 0 && col0 >= p.gather_col0 && grow >= 0)
+              later_scene = grow / p.gather_rows != (static_cast<long>(mt) * GEMM_BM) / p.gather_rows;
+          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 u;
@@ -487,6 +494,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             u.z = pack16x2<BF16>(v[c * 8 + 4], v[c * 8 + 5]);
             u.w = pack16x2<BF16>(v[c * 8 + 6], v[c * 8 + 7]);
             *reinterpret_cast<uint4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
+            if constexpr (EPI == EPI_QKV) {
+              if (later_scene) {
+                void* const* ptrs = reinterpret_cast<void* const*>(p.gather_maps + p.n_gather);
+                const long* lds = reinterpret_cast<const long*>(ptrs + p.n_gather);
+                const long scene = grow / p.gather_rows, rr = grow - scene * p.gather_rows;
+                const long off = scene * __ldg(lds + 1) + rr * __ldg(lds) + (col0 - p.gather_col0) + c * 8;
+                for (int r = 0; r < p.n_gather; ++r)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ptrs[r]) + off) = u;
+              }
+            }
+          }
+          if constexpr (EPI == EPI_QKV) {
+            if (later_scene) __threadfence_system();                      // peer stores visible before the cross-rank barrier
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
@@ -496,11 +516,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (EPI == EPI_QKV) {
               if (p.n_gather > 0 && col0 >= p.gather_col0) {             // K | V chunk: to every rank's gathered buffer too
                 const int row0 = mt * GEMM_BM, scene = row0 / p.gather_rows, r0 = row0 - scene * p.gather_rows;
-                const bool straddles = r0 + GEMM_BM > p.gather_rows && row0 + GEMM_BM > (scene + 1) * p.gather_rows && (scene + 1) * p.gather_rows < p.M;
-                for (int r = 0; r < p.n_gather; ++r) {
-                  tma_store_3d(&p.gather_maps[r], stg, col0 - p.gather_col0, r0, scene);
-                  if (straddles) tma_store_3d(&p.gather_maps[r], stg, col0 - p.gather_col0, r0 - p.gather_rows, scene + 1);
-                }
+                for (int r = 0; r < p.n_gather; ++r)
+                  tma_store_3d(&p.gather_maps[r], stg, col0 - p.gather_col0, r0, scene);      // clipped to this scene's rows
               }
             }
             tma_store_commit();

@@ -75,7 +75,8 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
 // Tensor maps for the fused K|V gather: dst[i] = address of THIS rank's first row inside rank i's gathered K|V buffer
 // ([scenes][world * rows][cols] 16-bit, row pitch ld elements; peer-mapped pointers); the map is 3-D {cols, rows, scenes}
 // with scene pitch `scene_ld` elements.  Writes n maps (128 bytes each) to `dev_maps` (device memory, 64-byte aligned)
-// with a synchronous copy - call once at setup, not inside a graph capture.
+// followed by the n raw pointers and (ld, scene_ld) as int64 (for the rows the epilogue stores directly, gemm.cuh), with a
+// synchronous copy - call once at setup, not inside a graph capture.  dev_maps: n * 136 + 16 bytes.
 extern "C" int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int64_t scenes,
                                    int64_t scene_ld, int dtype, void* dev_maps) {
   if (!dst || !dev_maps || n <= 0 || n > 16 || rows <= 0 || cols <= 0 || scenes <= 0 || (ld % 8) || (scene_ld % 8) ||
@@ -88,5 +89,11 @@ extern "C" int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_
     uint32_t box[3] = {64, (uint32_t)GEMM_BM, 1};
     if (make_tmap(&maps[i], dtype ? TM_BF16 : TM_F16, 3, dst[i], dims, str, box)) return -4;
   }
-  return (int)cudaMemcpy(dev_maps, maps, sizeof(CUtensorMap) * n, cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMemcpy(dev_maps, maps, sizeof(CUtensorMap) * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return (int)e;
+  int64_t tail[18];
+  for (int i = 0; i < n; ++i) tail[i] = reinterpret_cast<int64_t>(dst[i]);
+  tail[n] = ld; tail[n + 1] = scene_ld;
+  return (int)cudaMemcpy(static_cast<uint8_t*>(dev_maps) + sizeof(CUtensorMap) * n, tail, sizeof(int64_t) * (n + 2),
+                         cudaMemcpyHostToDevice);
 }

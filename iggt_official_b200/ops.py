@@ -132,7 +132,7 @@ def kv_gather_maps(dst_windows, rows, cols, ld, scenes, scene_ld, dtype, device)
     import ctypes
     n = len(dst_windows)
     ptrs = (ctypes.c_void_p * n)(*[d if isinstance(d, int) else d.data_ptr() for d in dst_windows])
-    dev = torch.empty(n * 128, dtype=torch.uint8, device=device)
+    dev = torch.empty(n * 136 + 16, dtype=torch.uint8, device=device)     # maps | raw pointers | ld, scene_ld
     with torch.cuda.device(device):
         st = _lib.load().iggt_kv_gather_maps(ctypes.cast(ptrs, ctypes.c_void_p), n, rows, cols, ld, scenes, scene_ld,
                                             F16 if dtype == torch.float16 else BF16, dev.data_ptr())

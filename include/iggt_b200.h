@@ -63,7 +63,8 @@ int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
  * rank's gathered K|V buffer as well - dst[i] = this rank's first row inside rank i's buffer ([scenes][world*rows][cols],
  * row pitch ld, scene pitch scene_ld elements), a peer-mapped pointer (torch symmetric memory over NVLink).  The
  * collective it replaces: one all-gather of K|V per global block (reference shape: iggt/models/aggregator.py:308-336,
- * attention over all S*T keys of a scene). */
+ * attention over all S*T keys of a scene).  dev_maps receives n * 136 + 16 bytes: the n maps, the n raw pointers and
+ * (ld, scene_ld) - rows of a tile that belong to a later scene than its first row are stored through the pointers. */
 int iggt_kv_gather_maps(void* const* dst, int n, int64_t rows, int64_t cols, int64_t ld, int64_t scenes, int64_t scene_ld,
                         int dtype, void* dev_maps);
 
