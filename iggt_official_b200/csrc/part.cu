@@ -3,8 +3,10 @@
 // (OCAB with 12x12 overlapping keys + relative-position bias and the reference's scrambled query windows;
 // HAB plain window self-attention), and the CAB channel-attention (squeeze-excite) pieces.
 // Reference: iggt/heads/adaptor.py:140-226, iggt/heads/part_head.py:148-243, iggt/heads/window_sa.py.
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "launch.cuh"
+#include "winattn.cuh"
 #include "../../include/iggt_b200.h"
 
 namespace iggt {
@@ -385,6 +387,13 @@ inline unsigned grid_cap(int64_t total, int threads = 256) {
 
 using namespace iggt;
 
+namespace {
+int winattn_tc() {
+  static const int v = [] { const char* e = getenv("IGGT_WINATTN_TC"); return e ? atoi(e) : 1; }();
+  return v;
+}
+}  // namespace
+
 extern "C" int iggt_layernorm16(const void* x, void* y, int64_t rows, int C, const float* w, const float* b,
                                 float eps, int dtype, iggt_stream_t stream) {
   if (rows <= 0) return 0;
@@ -416,8 +425,15 @@ extern "C" int iggt_ocab_attention(const void* q, const void* k, const void* v, 
   if (once.first()) {
     cudaFuncSetAttribute(ocab_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OCAB_SMEM);
     cudaFuncSetAttribute(ocab_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OCAB_SMEM);
+    cudaFuncSetAttribute(ocab_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OA_SMEM);
+    cudaFuncSetAttribute(ocab_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OA_SMEM);
   }
   const unsigned grid = static_cast<unsigned>(NB) * (h / 8) * (w / 8) * 4;
+  if (winattn_tc()) {      // tensor-core kernel (winattn.cuh); IGGT_WINATTN_TC=0 selects the scalar fp32 kernel below
+    if (dtype) ocab_attention_tc_kernel<true><<<grid, 128, OA_SMEM, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, table, rpi, (uint16_t*)out, h, w);
+    else ocab_attention_tc_kernel<false><<<grid, 128, OA_SMEM, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, table, rpi, (uint16_t*)out, h, w);
+    return (int)cudaGetLastError();
+  }
   if (dtype) ocab_attention_kernel<true><<<grid, 256, OCAB_SMEM, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, table, rpi, (uint16_t*)out, h, w);
   else ocab_attention_kernel<false><<<grid, 256, OCAB_SMEM, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, table, rpi, (uint16_t*)out, h, w);
   return (int)cudaGetLastError();
@@ -427,6 +443,11 @@ extern "C" int iggt_window_attention(const void* qkv, void* out, int NB, int h, 
                                      iggt_stream_t stream) {
   if (NB <= 0 || (h % 8) || (w % 8)) return -1;
   const unsigned grid = static_cast<unsigned>(NB) * (h / 8) * (w / 8) * 4;
+  if (winattn_tc()) {
+    if (dtype) window_attention_tc_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)qkv, (uint16_t*)out, h, w);
+    else window_attention_tc_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)qkv, (uint16_t*)out, h, w);
+    return (int)cudaGetLastError();
+  }
   if (dtype) window_attention_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)qkv, (uint16_t*)out, h, w);
   else window_attention_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)qkv, (uint16_t*)out, h, w);
   return (int)cudaGetLastError();

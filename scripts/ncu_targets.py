@@ -65,6 +65,16 @@ def targets():
     t["skinny_gemm_qkv"] = lambda: ops.skinny_gemm(xs, wsk, bsk)
     q8 = rnd(8, 6144, dtype=torch.float32)
     t["small_attention"] = lambda: ops.small_attention(q8, 1, 8, 16, 128)
+    from iggt_official_b200.heads.camera_head import CameraHead
+    from iggt_official_b200.layout import load_layout, populate
+    torch.manual_seed(0)
+    cam_mod = CameraHead()
+    populate(cam_mod, load_layout(), "camera_head.")
+    cam_mod = cam_mod.cuda()
+    pk = cam_mod._packed(DT, torch.device("cuda"))
+    cam_tok = rnd(8, 2048, dtype=torch.float32)
+    t["camera_head_one_launch"] = lambda: ops.camera_head(pk["cstruct"], pk, cam_tok, 1, 8, 4, DT)
+    t["attention_global_1of8_split3"] = lambda: ops.attention(qkv[:1374, :1024], qkv[:, 1024:2048], qkv[:, 2048:], 1, 1374, M, 16, splits=3)
     # ---- DPT heads
     f148 = rnd(S, 148, 148, 256)
     wc = rnd(256, 9 * 256, scale=1 / 48)
