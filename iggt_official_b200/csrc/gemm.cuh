@@ -24,7 +24,10 @@ enum GemmEpi : int {
   EPI_RESID32 = 1,   // out32 += gamma * (acc + bias)           (TMA reduce-add into the fp32 residual)
   EPI_QKV = 2,       // out16 = [rope(ln(q)) | rope(ln(k)) | v]  (per 64-wide head)
   EPI_STORE32 = 3,   // out32 = acc + bias
+  EPI_QKV_GATHER = 4,  // EPI_QKV + the K | V chunks also stored into every rank's gathered buffer (view sharding); a separate
+                       // instantiation so that the single-GPU qkv kernel carries none of it (it cost 22 % when it did)
 };
+__host__ __device__ constexpr bool epi_is_qkv(int e) { return e == EPI_QKV || e == EPI_QKV_GATHER; }
 
 struct GemmParams {
   int M, N, K;
@@ -301,7 +304,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* const vb = epi_vec;                  // this tile's bias   [BN]  (staged before the accumulator is ready)
     float* const vg = vb + BN;                  // this tile's gamma  [BN]  (EPI_RESID32)
     float* const vn = vb + BN;                  // q_norm w,b | k_norm w,b  [4][64]  (EPI_QKV, BN >= 128)
-    if constexpr (EPI == EPI_QKV) {
+    if constexpr (epi_is_qkv(EPI)) {
       if (p.qk_norm) {
         for (int i = gtid; i < 64; i += 128) {
           vn[i] = p.qn_w[i]; vn[64 + i] = p.qn_b[i]; vn[128 + i] = p.kn_w[i]; vn[192 + i] = p.kn_b[i];
@@ -349,7 +352,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
-      if constexpr (EPI == EPI_STORE16 || EPI == EPI_QKV) {
+      if constexpr (EPI == EPI_STORE16 || epi_is_qkv(EPI)) {
         const int nvalid = min(BN / 64, (p.N - n0 + 63) / 64);
         if (grp >= nvalid) {               // nothing to read for this group: release immediately
           tc_fence_before();
@@ -386,7 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[i] = lo.x; v[i + 1] = lo.y; v[i + 2] = hi.x; v[i + 3] = hi.y;
             }
           }
-          if constexpr (EPI == EPI_QKV) {
+          if constexpr (epi_is_qkv(EPI)) {
             if (p.qk_norm && col0 < 2 * p.C) {
               const bool is_k = col0 >= p.C;
               const float* nw = vn + (is_k ? 128 : 0);
@@ -482,7 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           // registers -> 128B-swizzled staging tile (row = 128 B = 64 x 16 bit)
           bool later_scene = false;                                       // EPI_QKV gather: this row is not in the tile's first scene
-          if constexpr (EPI == EPI_QKV) {
+          if constexpr (EPI == EPI_QKV_GATHER) {
             if (p.n_gather > 0 && col0 >= p.gather_col0 && grow >= 0)
               later_scene = grow / p.gather_rows != (static_cast<long>(mt) * GEMM_BM) / p.gather_rows;
           }
@@ -494,7 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             u.z = pack16x2<BF16>(v[c * 8 + 4], v[c * 8 + 5]);
             u.w = pack16x2<BF16>(v[c * 8 + 6], v[c * 8 + 7]);
             *reinterpret_cast<uint4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) = u;
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (EPI == EPI_QKV_GATHER) {
               if (later_scene) {
                 void* const* ptrs = reinterpret_cast<void* const*>(p.gather_maps + p.n_gather);
                 const long* lds = reinterpret_cast<const long*>(ptrs + p.n_gather);
@@ -505,7 +508,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          if constexpr (EPI == EPI_QKV) {
+          if constexpr (EPI == EPI_QKV_GATHER) {
             if (later_scene) __threadfence_system();                      // peer stores visible before the cross-rank barrier
           }
           fence_proxy_async_smem();
@@ -513,7 +516,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (leader) {
             if constexpr (CONV) tma_store_4d(&tmC, stg, col0, x0, y0, img);
             else tma_store_2d(&tmC, stg, col0, mt * GEMM_BM);
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (EPI == EPI_QKV_GATHER) {
               if (p.n_gather > 0 && col0 >= p.gather_col0) {             // K | V chunk: to every rank's gathered buffer too
                 const int row0 = mt * GEMM_BM, scene = row0 / p.gather_rows, r0 = row0 - scene * p.gather_rows;
                 for (int r = 0; r < p.n_gather; ++r)
@@ -590,7 +593,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (leader) {
       tma_store_wait_all<0>();
-      if constexpr (EPI == EPI_QKV) {
+      if constexpr (EPI == EPI_QKV_GATHER) {
         if (p.n_gather > 0) __threadfence_system();      // peer stores visible before the cross-rank barrier
       }
     }

@@ -76,7 +76,7 @@ inline GemmPlan plan_gemm(int epi, int M, int N, int K) {
 }
 
 // PAIR: p.num_m_tiles counts 256-row tile pairs and tB's box holds BN/2 weight rows (see gemm.cuh).
-template <int BN, int EPI, bool BF16, bool CONV, bool PAIR = false, int G = (EPI == EPI_QKV ? 1 : 2)>
+template <int BN, int EPI, bool BF16, bool CONV, bool PAIR = false, int G = (epi_is_qkv(EPI) ? 1 : 2)>
 inline int launch_gemm_kernel(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                               const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BN, EPI, BF16, CONV, G, PAIR>;

@@ -68,6 +68,9 @@ extern "C" int iggt_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t 
   if (make_tmap_2d(&tA, dt, A, M, K, lda, GEMM_BK, GEMM_BM)) return -4;
   if (make_tmap_2d(&tB, dt, W, N, K, ldw, GEMM_BK, pair ? bn / 2 : bn)) return -4;
   if (make_tmap_2d(&tC, dt, qkv, M, N, ldo, 64, GEMM_BM)) return -4;
+  if (n_gather > 0)
+    return dtype ? dispatch_bn<EPI_QKV_GATHER, true>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream)
+                 : dispatch_bn<EPI_QKV_GATHER, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
   return dtype ? dispatch_bn<EPI_QKV, true>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream)
                : dispatch_bn<EPI_QKV, false>(bn, pair, tA, tB, tC, p, (cudaStream_t)stream);
 }

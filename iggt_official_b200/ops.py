@@ -331,6 +331,9 @@ def skinny_gemm(x, w, bias=None, act=0, gamma=None, resid=None, out=None):
 
 
 def small_attention(qkv, B, N, H, d):
+    if N > 256 or (2 * N * d + 4 * N) * 4 > 200 * 1024:
+        raise ValueError(f"the camera head's token attention keeps all {N} views' keys and values of a head in shared memory "
+                         f"(<= 256 views, <= {200 * 1024 // (8 * d + 16)} at head dim {d}); split the scene into fewer views per call")
     out = torch.empty((B * N, H * d), dtype=torch.float32, device=qkv.device)
     _call(qkv, "iggt_small_attention", 4.0 * B * N * N * H * d, 16.0 * B * N * H * d,
           qkv.data_ptr(), out.data_ptr(), B, N, H, d, float(d) ** -0.5, _STREAM)

@@ -55,4 +55,8 @@ def test_demo1_images_through_loader_model_and_postprocess():
         err = ((predictions[k] - ref[k]).norm() / ref[k].norm()).item()
         assert err < 2e-2, (k, err)                                                    # bf16 trunk: see test_fullsize_parity_gpu.py
     we, wi = ref_model.pose_encoding_to_extri_intri(pose, (H, W))
-    assert (extrinsic - we).abs().max().item() < 1e-5 and (intrinsic - wi).abs().max().item() < 1e-3
+    assert (extrinsic - we).abs().max().item() < 1e-5
+    # synthetic weights can put the ReLU'd field of view at exactly 0, i.e. an infinite focal length - in both
+    fin = torch.isfinite(wi)
+    assert torch.equal(torch.isfinite(intrinsic), fin) and torch.equal(intrinsic[~fin], wi[~fin])
+    assert ((intrinsic[fin] - wi[fin]).abs() / wi[fin].abs().clamp_min(1.0)).max().item() < 1e-5

@@ -77,3 +77,11 @@ def test_cabi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in iggt_b200.h but not exported"
     assert declared - {"iggt_version"} == set(_lib.SIGNATURES.keys())
+
+
+def test_small_attention_view_limit_is_a_clear_error():
+    """more views than the camera head's token attention holds in shared memory must raise a descriptive
+    error, not a bare launcher status (checked before any device work, so it runs without a GPU)."""
+    from iggt_official_b200 import ops
+    with pytest.raises(ValueError, match="views"):
+        ops.small_attention(torch.zeros(1, 3 * 2048), 1, 300, 16, 128)
