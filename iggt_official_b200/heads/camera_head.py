@@ -119,11 +119,19 @@ class CameraHead(Node):
         dt = compute_dtype or (torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float16)
         pk = self._packed(dt, dev)
         M = B * S
-        if FUSED and M <= 16 and camera_tokens.is_cuda:
+        if FUSED and S <= 16 and camera_tokens.is_cuda:
             rows = camera_tokens.reshape(M, C)                    # a strided view of tokens[:, :, 0]: no copy
             if rows.dtype != torch.float32 or rows.stride(1) != 1:
                 rows = rows.float().contiguous()
-            poses = ops.camera_head(pk["cstruct"], pk, rows, B, S, num_iterations, dt)
+            if M <= 16:
+                poses = ops.camera_head(pk["cstruct"], pk, rows, B, S, num_iterations, dt)
+            else:
+                # scenes only meet in nothing here (the token attention is per scene): one launch per group of scenes
+                # that fits the kernel's 16 rows - the weights are re-streamed per group (1.4 ms each), still well under
+                # the ~180 launches of the layer-by-layer path
+                per = max(1, 16 // S)
+                poses = torch.cat([ops.camera_head(pk["cstruct"], pk, rows[b0 * S:(b0 + per) * S], min(per, B - b0), S,
+                                                   num_iterations, dt) for b0 in range(0, B, per)], 1)
             return [poses[i].view(B, S, 9) for i in range(num_iterations)]
         raw = camera_tokens.reshape(M, C).float().contiguous()
         pt = torch.empty_like(raw)

@@ -24,7 +24,7 @@ def setup():
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,S", [(1, 8), (1, 3), (2, 4), (1, 1), (1, 13), (2, 8), (4, 4)])
+@pytest.mark.parametrize("B,S", [(1, 8), (1, 3), (2, 4), (1, 1), (1, 13), (2, 8), (4, 4), (4, 16), (5, 3)])
 def test_fused_camera_head_matches_layer_path_and_oracle(setup, dtype, B, S):
     from iggt_official_b200.heads import camera_head as CH
     from oracle import ref_model
