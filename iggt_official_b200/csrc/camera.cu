@@ -206,17 +206,22 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
         const int g = lane >> 2, tq = lane & 3;
         const float* gam = lnbuf + lslot * 2 * CAM_DIM;
         if (P.ln == 1 && cta < tiles) mbar_wait(&ln_full[lslot], lph);    // gamma | beta are in shared memory
-        for (int t = cta; t < tiles; t += G) {
-          float acc[2][4];                                                // two n-tiles (8 columns each) x (rows g, g + 8)
+        // chunk-major over this CTA's tiles (<= 4): an activation chunk is staged ONCE and every tile consumes its weight
+        // stages of that chunk (the accumulators of all tiles live in registers across chunks)
+        const int ntl = cta < tiles ? (tiles - cta + G - 1) / G : 0;
+        float acc[4][2][4];
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+            for (int i = 0; i < 4; ++i) acc[ti][c][i] = 0.f;
+        if (ntl > 0) {
           for (int ch = 0; ch < nchunks; ++ch) {
             const int k0 = ch * KX;
             const int kn = min(KX, P.K - k0);                             // k of this chunk (16, 1024, 2048)
             const int kst = (kn + 15) & ~15;                              // staged extent: whole k steps
-            if (t == cta || nchunks > 1) {
+            {
               // ---- stage the activations as 16-bit planes hi | lo, [row][KXP], LayerNorm applied on the way
               named_bar_sync(2, 256);                                     // previous readers of xs are done
               for (int m = warp; m < MP; m += 8) {
@@ -268,8 +273,11 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
                 }
               }
               named_bar_sync(2, 256);
-              if (stamp && t == cta && ch == 0) stamp[1] = cam_now();
+              if (stamp && ch == 0) stamp[1] = cam_now();
             }
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti) {
+              if (ti < ntl) {
             // ---- weight stages of this chunk (1024 k each)
             for (int ks = 0; ks < (kn + CAM_KS - 1) / CAM_KS; ++ks) {
               mbar_wait(&full[st], ph);
@@ -298,8 +306,8 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
                     const uint8_t* wr = wst + q64 * (CAM_COLS * 128) + col * 128 + tq * 4;
                     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr + ((j ^ (col & 7)) << 4));
                     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + (((j + 1) ^ (col & 7)) << 4));
-                    cam_mma<BF16>(acc[c], ah0, ah1, ah2, ah3, b0, b1);
-                    cam_mma<BF16>(acc[c], al0, al1, al2, al3, b0, b1);
+                    cam_mma<BF16>(acc[ti][c], ah0, ah1, ah2, ah3, b0, b1);
+                    cam_mma<BF16>(acc[ti][c], al0, al1, al2, al3, b0, b1);
                   }
                 }
               }
@@ -307,14 +315,21 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               if (lane == 0) mbar_arrive(&empty[st]);
               if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
             }
+              }
+            }
           }
+        }
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti) {
+          if (ti >= ntl) break;
+          const int t = cta + ti * G;
           // ---- reduce the 8 warps' k slices through shared memory; thread (m, c) finishes one output element
           named_bar_sync(2, 256);                                         // the previous tile's sums have been read
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float* r0 = red + (warp * 16 + g) * CAM_COLS + c * 8 + 2 * tq;
-            *reinterpret_cast<float2*>(r0) = make_float2(acc[c][0], acc[c][1]);
-            *reinterpret_cast<float2*>(r0 + 8 * CAM_COLS) = make_float2(acc[c][2], acc[c][3]);
+            *reinterpret_cast<float2*>(r0) = make_float2(acc[ti][c][0], acc[ti][c][1]);
+            *reinterpret_cast<float2*>(r0 + 8 * CAM_COLS) = make_float2(acc[ti][c][2], acc[ti][c][3]);
           }
           named_bar_sync(2, 256);
           {

@@ -83,3 +83,50 @@ def test_more_than_12_views_works(models):
     m.compute_dtype = torch.float16
     out = m(torch.rand(13, 3, 28, 28, device="cuda"))
     assert out["depth"].shape == (1, 13, 28, 28, 1) and torch.isfinite(out["depth"]).all()
+
+
+def test_head_activation_range_switches_on_the_kernels():
+    """The activation-range scenario of tests/test_model_wiring.py on the real kernels: fp16 heads overflow, `check_finite`
+    raises, bf16 heads (fp32's exponent range) stay finite and agree with the fp32 oracle to bf16 precision."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_model_wiring import _range_stress_state_dict
+    from oracle import ref_model
+    from iggt_official_b200.models.vggt import VGGT
+    sd = _range_stress_state_dict()
+    m = VGGT()
+    m.load_state_dict(sd, strict=False)
+    m.eval().to("cuda")
+    m.compute_dtype = torch.float16
+    images = torch.rand(2, 3, 28, 42, generator=torch.Generator().manual_seed(5)).cuda()
+    assert not torch.isfinite(m(images)["depth"]).all()
+    m.check_finite = True
+    with pytest.raises(FloatingPointError, match="head_dtype = torch.bfloat16"):
+        m(images)
+    m.head_dtype = torch.bfloat16
+    out = m(images)
+    ref = ref_model.forward({k: v.cuda() for k, v in sd.items()}, images, model="vggt", amp=torch.float16, skip_part=True)
+    assert _l2(out["depth"], ref["depth"]) < 3e-2 and _l2(out["world_points"], ref["world_points"]) < 6e-2
+
+
+def test_model_on_a_second_device_without_set_device():
+    """launches follow the tensors' device (`model.to("cuda:1")` with device 0 current), incl. the per-device
+    kernel configuration; needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import weights
+    from iggt_official_b200.models.vggt import VGGT
+    sd = weights.make_state_dict(2, "default", prefixes=("aggregator.", "camera_head.", "depth_head.", "point_head."))
+    images = torch.rand(2, 3, 42, 56, generator=torch.Generator().manual_seed(7))
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = VGGT()
+        m.load_state_dict(sd, strict=False)
+        m.eval().to(dev)
+        m.compute_dtype = torch.float16
+        assert torch.cuda.current_device() == 0
+        o = m(images.to(dev))
+        assert o["depth"].device == torch.device(dev)
+        outs.append({k: (torch.stack(v) if isinstance(v, list) else v).cpu() for k, v in o.items()})
+    for k in ("depth", "world_points", "pose_enc"):
+        assert _l2(outs[1][k], outs[0][k]) < 1e-4, k

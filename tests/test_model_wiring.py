@@ -57,3 +57,44 @@ def test_cpu_tensors_are_refused_without_the_hook():
     from iggt_official_b200.models.vggt import VGGT
     with pytest.raises(RuntimeError, match="CUDA"):
         VGGT()(torch.zeros(1, 3, 28, 28))
+
+
+def _range_stress_state_dict(k=2e5):
+    """Head activations k x larger than any fp16 can hold, the last 1x1 scaled back by 1 / k: the outputs stay O(1)."""
+    sd = weights.make_state_dict(2, "default", prefixes=("aggregator.", "camera_head.", "depth_head.", "point_head."))
+    for h in ("depth_head.", "point_head."):
+        for i in range(4):
+            sd[h + f"projects.{i}.weight"] = sd[h + f"projects.{i}.weight"] * k
+            sd[h + f"projects.{i}.bias"] = sd[h + f"projects.{i}.bias"] * k
+        sd[h + "scratch.output_conv2.2.weight"] = sd[h + "scratch.output_conv2.2.weight"] / k
+    return sd
+
+
+def test_head_activation_range_switches(monkeypatch):
+    """ADVICE r1 (fp16 heads vs a checkpoint with large activations): with activations beyond 65504 the default fp16 heads
+    return inf / nan - `check_finite` turns that into a FloatingPointError naming the remedy, and `head_dtype = bfloat16`
+    (fp32's exponent range) computes the same network finitely.  Host logic on the CPU with emulated launchers; the same
+    scenario runs on the real kernels in tests/test_model_gpu.py."""
+    from iggt_official_b200 import ops
+    from iggt_official_b200.models import aggregator as agg_mod
+    from iggt_official_b200.models.vggt import VGGT
+    for name, fn in EMU.items():
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(agg_mod, "_require_cuda", lambda images: None)
+    m = VGGT()
+    m.load_state_dict(_range_stress_state_dict(), strict=False)
+    m.eval()
+    m.compute_dtype = torch.float32
+    images = torch.rand(2, 3, 28, 42, generator=torch.Generator().manual_seed(5))
+    m.head_dtype = torch.float32
+    ref = m(images)
+    m.head_dtype = torch.float16
+    m.invalidate_packed()
+    assert not torch.isfinite(m(images)["depth"]).all()
+    m.check_finite = True
+    with pytest.raises(FloatingPointError, match="head_dtype = torch.bfloat16"):
+        m(images)
+    m.head_dtype = torch.bfloat16
+    m.invalidate_packed()
+    out = m(images)                                           # check_finite still on: must pass
+    assert _l2(out["depth"], ref["depth"]) < 3e-2 and _l2(out["world_points"], ref["world_points"]) < 6e-2
