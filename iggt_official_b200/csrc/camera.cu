@@ -172,13 +172,16 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
             tma_bulk_load_1d(lnbuf + lslot * 2 * CAM_DIM + CAM_DIM, P.ln_b, CAM_DIM * 4, &ln_full[lslot]);
             if (++lslot == 2) { lslot = 0; lph ^= 1; }
           }
-          for (int t = cta; t < tiles; t += G)
-            for (int ks = 0; ks < nst; ++ks) {
-              mbar_wait(&empty[st], ph ^ 1);
-              mbar_expect_tx(&full[st], CAM_W_BYTES);       // the box is always 32 KB (out-of-range k groups / columns: zeros)
-              tma_load_3d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], 0, t * CAM_COLS, ks * (CAM_KS / 64));
-              if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
-            }
+          // the consumers' order: activation chunk (KX k = SPC stages) -> this CTA's tiles -> the chunk's stages
+          constexpr int SPC = KX / CAM_KS;
+          for (int s0 = 0; s0 < nst; s0 += SPC)
+            for (int t = cta; t < tiles; t += G)
+              for (int ks = s0; ks < min(s0 + SPC, nst); ++ks) {
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], CAM_W_BYTES);     // the box is always 32 KB (out-of-range k groups / columns: zeros)
+                tma_load_3d(sW + st * CAM_W_BYTES, &prog.maps[P.tm], &full[st], 0, t * CAM_COLS, ks * (CAM_KS / 64));
+                if (++st == CAM_STAGES) { st = 0; ph ^= 1; }
+              }
         }
     }
     return;
@@ -345,7 +348,7 @@ camera_head_kernel(const __grid_constant__ CamProgram prog) {
               if (P.gamma) v *= P.gamma[n];
               if (P.flags & CF_POSE_OUT) {
                 if (it > 0) v += P.out[m * P.ldo + n];                    // pred += delta
-                P.out2[(static_cast<long>(it) * M + m) * 9 + n] = n >= 7 ? fmaxf(v, 0.f) : v;   // activate_pose
+                P.out2[(static_cast<long>(it) * M + m) * 9 + n] = n >= 7 ? relu_nan(v) : v;   // activate_pose
               } else if (P.resid) {
                 v += P.resid[m * P.ldr + n];
               }

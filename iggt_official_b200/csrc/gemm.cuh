@@ -107,7 +107,7 @@ __device__ __forceinline__ float round16(float x) {
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return gelu_fast(x);
-  if (act == 2) return fmaxf(x, 0.0f);
+  if (act == 2) return relu_nan(x);
   if (act == 3) return x > 0.0f ? x : 0.01f * x;
   return x;
 }

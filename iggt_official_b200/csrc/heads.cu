@@ -276,7 +276,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     if (n < N && m < M) {
       v += bias ? bias[n] : 0.f;
       if (act == 1) v = gelu_erf(v);
-      else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 2) v = relu_nan(v);
       else if (act == 4) v = v / (1.0f + expf(-v));  // SiLU
       v *= gamma ? gamma[n] : 1.f;
       if (resid) v += resid[m * ldr + n];

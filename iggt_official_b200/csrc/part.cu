@@ -345,7 +345,7 @@ se_scale_add_kernel(const uint16_t* __restrict__ y0, const uint16_t* __restrict_
   if (threadIdx.x < R) {
     float a = b1[threadIdx.x];
     for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], mean[static_cast<int64_t>(n) * C + c], a);
-    s_hid[threadIdx.x] = fmaxf(a, 0.f);
+    s_hid[threadIdx.x] = relu_nan(a);
   }
   __syncthreads();
   if (threadIdx.x < C) {

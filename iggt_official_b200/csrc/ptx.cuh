@@ -299,6 +299,12 @@ __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
   if constexpr (BF16) return pack_bf16x2(a, b);
   else return pack_f16x2(a, b);
 }
+// ReLU that keeps a NaN (torch.relu's behaviour; fmaxf would return 0 and hide an overflowed head activation)
+__device__ __forceinline__ float relu_nan(float x) {
+  float y;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -175,7 +175,7 @@ tailconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (y < p.H && x < p.W) {
         float f[TC_N];
 #pragma unroll
-        for (int i = 0; i < TC_N; ++i) f[i] = fmaxf(__uint_as_float(r[i]) + s_bias[i], 0.f);     // conv bias + ReLU
+        for (int i = 0; i < TC_N; ++i) f[i] = relu_nan(__uint_as_float(r[i]) + s_bias[i]);     // conv bias + ReLU
         const int64_t pix = (static_cast<int64_t>(img) * p.H + y) * p.W + x;
         if (!p.w2) {
           uint16_t* dst = reinterpret_cast<uint16_t*>(p.out16) + pix * TC_N;

@@ -129,6 +129,29 @@ def gather_camera_tokens(tokens23: torch.Tensor, group, world: int) -> torch.Ten
     return recv.permute(1, 0, 2, 3).reshape(B, world * S_loc, C).contiguous()
 
 
+def camera_poses(model, tokens, cam: torch.Tensor, rank: int, world: int, group, hd, iters: int = 4):
+    """Camera head of the view-sharded forward.  `cam` [B, S, 2048]: the gathered camera tokens.  The head only couples the
+    views of ONE scene (reference iggt/heads/camera_head.py:114-121: attention over S), so with B >= 2 scenes every rank
+    refines ceil(B / world) of them and the poses (iters x B x S x 9 floats) are all-gathered - instead of every rank
+    streaming the head's 216 M parameters once per group of scenes.  B = 1 (and IGGT_CAMERA_BY_SCENE=0): replicated."""
+    import os
+    B, S, _ = cam.shape
+    if world == 1 or B < 2 or os.environ.get("IGGT_CAMERA_BY_SCENE", "1") == "0":
+        return model.camera_head(tokens, num_iterations=iters, compute_dtype=hd, camera_tokens=cam)
+    q = -(-B // world)                                                     # scenes per rank (the last ranks may own none)
+    b0, b1 = min(rank * q, B), min((rank + 1) * q, B)
+    mine = torch.zeros((iters, q, S, 9), dtype=torch.float32, device=cam.device)
+    if b1 > b0:
+        poses = model.camera_head(tokens, num_iterations=iters, compute_dtype=hd, camera_tokens=cam[b0:b1].contiguous())
+        mine[:, :b1 - b0] = torch.stack(poses)
+    ev = _trace_begin()
+    allp = torch.empty((world,) + tuple(mine.shape), dtype=torch.float32, device=cam.device)
+    dist.all_gather_into_tensor(allp.view(-1), mine.view(-1), group=group)
+    _trace_end(ev, "nccl_all_gather_poses", (world + 1) * mine.numel() * 4.0)
+    full = allp.permute(1, 0, 2, 3, 4).reshape(iters, world * q, S, 9)[:, :B]
+    return [full[i].contiguous() for i in range(iters)]
+
+
 def shard_views(model, group=None):
     """Configure `model` (IGGT / VGGT) for view-sharded execution over `group` (default: WORLD)."""
     if not dist.is_initialized():
@@ -166,7 +189,7 @@ def forward_sharded(model, images_local: torch.Tensor, rank: int, world: int, gr
     tokens, psi = model.aggregator(images_local, compute_dtype=dt, view_offset=rank * S_loc,
                                    total_views=world * S_loc)
     cam = gather_camera_tokens(tokens[23], group, world)
-    pred = {"pose_enc": model.camera_head(tokens, compute_dtype=hd, camera_tokens=cam)}
+    pred = {"pose_enc": camera_poses(model, tokens, cam, rank, world, group, hd)}
     d, dc = model.depth_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=hd)
     out = model.point_head(tokens, images=images_local, patch_start_idx=psi, compute_dtype=hd)
     pred["depth"], pred["depth_conf"] = d, dc

@@ -43,6 +43,30 @@ def test_gemm_store16(ops, dtype, M, N, K, act):
     assert _relmax(out, ref) < 2 * _tol(dtype)
 
 
+def test_relu_epilogues_keep_nan_like_torch(ops):
+    """torch.relu(nan) = nan, relu(-inf) = 0, relu(inf) = inf: an overflowed fp16 head activation must stay visible through
+    the ReLU epilogues (fmaxf would turn inf - inf into 0 and hand `check_finite` finite garbage)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(128, 64, device="cuda", generator=g).half()
+    a[5, 0], a[5, 1] = float("inf"), float("-inf")             # row 5: inf - inf = nan in every column
+    a[9, 0] = float("inf")                                     # row 9: +-inf by the sign of w[:, 0]
+    w = (torch.randn(64, 64, device="cuda", generator=g) / 8).half()
+    w[:, :2] = w[:, :2].abs() + 0.1
+    w[::2, 0] *= -1
+    out = ops.gemm_store16(a, w, torch.zeros(64, device="cuda"), act=2).float()
+    ref = F.relu(a.float() @ w.float().t())
+    torch.cuda.synchronize()
+    assert torch.isnan(out[5]).all() and torch.isnan(ref[5]).all()
+    assert torch.equal(torch.isinf(out[9]), torch.isinf(ref[9])) and (out[9][::2] == 0).all()
+    x = torch.randn(1, 8, 8, 64, device="cuda", generator=g).half()
+    x[0, 3, 3, 0], x[0, 3, 3, 1] = float("inf"), float("-inf")
+    wc = (torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24).half()
+    wc[:, :2] = wc[:, :2].abs() + 0.1
+    wp = wc.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous()
+    y = ops.conv_nhwc(x, wp, torch.zeros(64, device="cuda"), act=2).float()
+    assert torch.isnan(y[0, 2:5, 2:5]).all() and torch.isfinite(y[0, 6:, 6:]).all()
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_store16_addend(ops, dtype):
     M, N, K, R = 3 * 361, 256, 2048, 361
