@@ -74,6 +74,8 @@ def targets():
     pk = cam_mod._packed(DT, torch.device("cuda"))
     cam_tok = rnd(8, 2048, dtype=torch.float32)
     t["camera_head_one_launch"] = lambda: ops.camera_head(pk["cstruct"], pk, cam_tok, 1, 8, 4, DT)
+    cam_tok16 = rnd(16, 2048, dtype=torch.float32)
+    t["camera_head_one_launch_16_rows"] = lambda: ops.camera_head(pk["cstruct"], pk, cam_tok16, 1, 16, 4, DT)
     t["attention_global_1of8_split3"] = lambda: ops.attention(qkv[:1374, :1024], qkv[:, 1024:2048], qkv[:, 2048:], 1, 1374, M, 16, splits=3)
     # ---- DPT heads
     f148 = rnd(S, 148, 148, 256)
